@@ -1,0 +1,293 @@
+"""Seeded test cases, written once and run against any implementation (see apis.py).
+
+Every case takes an ``api`` namespace and returns a flat dict of numpy arrays /
+scalars.  ``tests/golden/make_golden.py`` runs them on the real reference and
+stores the results; the CPU tests replay them on the oracle (bit-exact), the GPU
+tests replay them on the CUDA path (tolerances in test_gpu_parity.py).
+"""
+from functools import partial
+
+import numpy as np
+
+from proxmin_b200 import workloads
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+# --------------------------------------------------------------------------
+# operators
+# --------------------------------------------------------------------------
+
+def edge_array(dtype=np.float32):
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal((6, 40)).astype(dtype)
+    x[0, :8] = [0.0, -0.0, 0.25, -0.25, 1e-30, -1e-30, 0.5, -0.5]
+    x[1, :4] = [np.inf, -np.inf, np.nan, 3.0]
+    return x
+
+
+OPS = [
+    ("plus", "prox_plus", {}),
+    ("zero", "prox_zero", {}),
+    ("id", "prox_id", {}),
+    ("min_rel", "prox_min", dict(thresh=0.5)),
+    ("min_abs", "prox_min", dict(thresh=-0.3, type="absolute")),
+    ("max_rel", "prox_max", dict(thresh=0.5)),
+    ("max_abs", "prox_max", dict(thresh=0.25, type="absolute")),
+    ("hard_rel", "prox_hard", dict(thresh=0.5)),
+    ("hard_abs", "prox_hard", dict(thresh=0.25, type="absolute")),
+    ("hard_plus", "prox_hard_plus", dict(thresh=0.5)),
+    ("soft_rel", "prox_soft", dict(thresh=0.5)),
+    ("soft_abs", "prox_soft", dict(thresh=0.25, type="absolute")),
+    ("soft_plus", "prox_soft_plus", dict(thresh=0.5)),
+]
+
+
+@case
+def operators_elementwise(api):
+    out = {}
+    for tag, name, kw in OPS:
+        x = edge_array()
+        out[tag] = np.array(getattr(api, name)(x, 0.5, **kw))
+    return out
+
+
+@case
+def operators_unity(api):
+    rng = np.random.default_rng(3)
+    base = (rng.random((16, 96)) + 0.05).astype(np.float32)
+    signed = rng.standard_normal((16, 96)).astype(np.float32)
+    out = {}
+    for ax in (0, 1):
+        out["unity_ax%d" % ax] = np.array(api.prox_unity(base.copy(), 1.0, axis=ax))
+        out["unity_plus_ax%d" % ax] = np.array(api.prox_unity_plus(signed.copy(), 1.0, axis=ax))
+    ap = api.AlternatingProjections([api.prox_unity, api.prox_plus])  # plus first, then unity
+    out["altproj"] = np.array(ap(signed.copy(), 1.0))
+    ap2 = api.AlternatingProjections([partial(api.prox_max, thresh=0.1, type="absolute"), api.prox_plus], repeat=2)
+    out["altproj2"] = np.array(ap2(signed.copy(), 1.0))
+    return out
+
+
+# --------------------------------------------------------------------------
+# generic solvers on the reference's own example problem (examples/parabola.py)
+# --------------------------------------------------------------------------
+
+_dX = np.array([1, 0.5])
+
+
+def _grad_f(X):
+    return 2 * (X - _dX)
+
+
+def _step_f(X, it=0):
+    return 0.1 * 1 / 2
+
+
+def _prox_circle(X, step):
+    phi = np.arctan2(X[1], X[0])
+    return 0.5 * np.array([np.cos(phi), np.sin(phi)])
+
+
+def _prox_line(X, step):
+    return np.array([min(X[0], 0.5), min(X[1], -0.75)])
+
+
+def _prox_gradf(X, step):
+    return X - step * _grad_f(X)
+
+
+def _parabola(api, prox):
+    X0 = np.array([-1.0, -1])
+    out = {}
+    mi = 1000
+    X = X0.copy(); api.pgm(X, _grad_f, _step_f, max_iter=mi); out["pgm_free"] = X
+    X = X0.copy(); api.pgm(X, _grad_f, _step_f, prox=prox, max_iter=mi); out["pgm"] = X
+    X = X0.copy(); api.pgm(X, _grad_f, _step_f, prox=prox, max_iter=mi, accelerated=True); out["apgm"] = X
+    for scheme in ["adam", "nadam", "adamx", "amsgrad", "padam", "radam"]:
+        X = X0.copy()
+        b1 = 0.0
+        if scheme != "adam":
+            b1 = b1 ** np.arange(1, mi + 1)
+        api.adaprox(X, _grad_f, _step_f, prox=prox, b1=b1, b2=0.5, max_iter=mi, scheme=scheme, p=0.125)
+        out[scheme] = X
+    X = X0.copy(); api.admm(X, _prox_gradf, _step_f, prox_g=prox, max_iter=mi); out["admm"] = X
+    X = X0.copy()
+    api.admm(X, lambda X, s: prox(_prox_gradf(X, s), s), _step_f, prox_g=None, max_iter=mi)
+    out["admm_direct"] = X
+    X = X0.copy(); api.sdmm(X, _prox_gradf, _step_f, proxs_g=[prox] * 2, max_iter=mi); out["sdmm"] = X
+    return out
+
+
+@case
+def parabola_circle(api):
+    return _parabola(api, _prox_circle)
+
+
+@case
+def parabola_line(api):
+    return _parabola(api, _prox_line)
+
+
+# --------------------------------------------------------------------------
+# NMF hot path
+# --------------------------------------------------------------------------
+
+def _pack(api, A, S, extra=None):
+    n, sub = api.iterations()
+    out = {"A": A, "S": S, "iterations": np.int64(n if n is not None else -1)}
+    if sub is not None:
+        out["sub_iterations"] = np.array(sub, dtype=np.int64)
+    if extra:
+        out.update(extra)
+    return out
+
+
+@case
+def nmf_pgm_cfg1(api):
+    """BASELINE config 1 (256x512, K=8, plus/plus) for 100 fixed iterations."""
+    Y, A, S = workloads.cfg1()
+    conv, G, st = api.nmf.nmf(Y, A, S, max_iter=100, e_rel=0)
+    return _pack(api, A, S, {"G_A": G[0], "G_S": G[1], "step_A": np.float64(st[0]), "step_S": np.float64(st[1])})
+
+
+@case
+def nmf_pgm_cfg1_converge(api):
+    """Same data, default e_rel=1e-3: the stopping iteration is part of parity."""
+    Y, A, S = workloads.cfg1()
+    conv, G, st = api.nmf.nmf(Y, A, S, max_iter=1000)
+    return _pack(api, A, S, {"converged": np.array(conv, dtype=bool)})
+
+
+@case
+def nmf_pgm_unity(api):
+    """cfg2 recipe scaled down, prox_A=plus, prox_S=unity_plus (columns of S sum to one)."""
+    Y, A, S = workloads.cfg2(128, 384, 16, seed=5)
+    api.nmf.nmf(Y, A, S, prox_A=api.prox_plus, prox_S=api.prox_unity_plus, max_iter=60, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_pgm_altproj(api):
+    """The AlternatingProjections spelling of unity_plus must give the same path."""
+    Y, A, S = workloads.cfg2(128, 384, 16, seed=5)
+    pS = api.AlternatingProjections([api.prox_unity, api.prox_plus])
+    api.nmf.nmf(Y, A, S, prox_A=api.prox_plus, prox_S=pS, max_iter=60, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_pgm_accel(api):
+    """Nesterov-accelerated block PGM (algorithms.py:93-95) through the generic ``pgm`` entry point.
+
+    The reference's accelerated NMF diverges with the plain Lipschitz steps, so the
+    steps are halved by a user step function (a user callable: the generic path)."""
+    Y, A, S = workloads.cfg1(96, 200, 6, seed=11)
+
+    def step(*X, it=None):
+        return tuple(0.5 * s for s in api.nmf.step_pgm(*X))
+
+    api.pgm([A, S], partial(api.nmf.grad_likelihood, Y=Y), step, prox=[api.prox_plus] * 2,
+            max_iter=60, e_rel=0, accelerated=True)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_pgm_soft(api):
+    """L1-regularised S (prox_soft_plus, relative threshold scales with the Lipschitz step)."""
+    Y, A, S = workloads.cfg1(96, 200, 6, seed=12)
+    api.nmf.nmf(Y, A, S, prox_S=partial(api.prox_soft_plus, thresh=0.5), max_iter=60, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_pgm_ragged(api):
+    """Shapes that are not multiples of any tile size."""
+    Y, A, S = workloads.cfg1(77, 203, 5, seed=13)
+    api.nmf.nmf(Y, A, S, max_iter=40, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_adaprox_amsgrad(api):
+    """config 3 recipe scaled down: adaprox/AMSGrad, plus/plus, default step_adaprox."""
+    Y, A, S = workloads.cfg2(128, 384, 16, seed=6)
+    conv, M, V, Vh = api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", max_iter=40,
+                                 check_convergence=False)
+    return _pack(api, A, S, {"M_A": M[0], "V_S": V[1]})
+
+
+@case
+def nmf_adaprox_amsgrad_unity(api):
+    Y, A, S = workloads.cfg2(128, 384, 16, seed=6)
+    api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", prox_S=api.prox_unity_plus,
+                max_iter=40, check_convergence=False)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_adaprox_schemes(api):
+    out = {}
+    for scheme in ["adam", "nadam", "padam", "adamx"]:
+        Y, A, S = workloads.cfg2(64, 192, 8, seed=7)
+        api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme=scheme, max_iter=25, e_rel=1e-3)
+        n, sub = api.iterations()
+        out[scheme + "_A"], out[scheme + "_S"] = A, S
+        out[scheme + "_iterations"] = np.int64(n)
+        out[scheme + "_sub"] = np.array(sub, dtype=np.int64)
+    return out
+
+
+@case
+def nmf_bsdmm(api):
+    """config 5 recipe scaled down: bsdmm, direct prox_id, constraints via proxs_g."""
+    Y, A, S = workloads.cfg5(96, 256, 8, seed=9)
+    proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus, partial(api.prox_soft, thresh=0.01)]]
+    conv = api.nmf.nmf(Y, A, S, algorithm=api.bsdmm, prox_A=api.prox_id, prox_S=api.prox_id,
+                       proxs_g=proxs_g, max_iter=20, e_rel=1e-6)
+    return _pack(api, A, S, {"converged": np.array([bool(c) for c in conv])})
+
+
+@case
+def grad_and_loss(api):
+    Y, A, S = workloads.cfg2(200, 333, 24, seed=21)
+    gA, gS = api.nmf.grad_likelihood(A, S, Y=Y)
+    return {"G_A": gA, "G_S": gS, "loss": np.float64(api.nmf.log_likelihood(A, S, Y=Y)),
+            "step_A": np.float64(api.nmf.step_pgm(A, S)[0]), "step_S": np.float64(api.nmf.step_pgm(A, S)[1])}
+
+
+# --------------------------------------------------------------------------
+# ADMM LASSO (BASELINE config 4 scaled down)
+# --------------------------------------------------------------------------
+
+def lasso_callables(api, b):
+    def prox_f(X, s):  # README gradient-step pattern for f = 0.5 ||X - b||^2
+        return X - s * (X - b)
+
+    def step_f(X, it=None):
+        return 0.5
+
+    return prox_f, step_f, partial(api.prox_soft, thresh=0.5)
+
+
+@case
+def admm_lasso(api):
+    b, X = workloads.cfg4(10_000, seed=7)
+    prox_f, step_f, prox_g = lasso_callables(api, b)
+    conv, err = api.admm(X, prox_f, step_f, prox_g=prox_g, max_iter=200, e_rel=1e-6)
+    n, _ = api.iterations()
+    return {"X": X, "converged": np.bool_(conv), "errors": np.array(err, dtype=np.float64),
+            "iterations": np.int64(n)}
+
+
+@case
+def sdmm_lasso_plus(api):
+    b, X = workloads.cfg4(10_000, seed=8)
+    prox_f, step_f, prox_g = lasso_callables(api, b)
+    conv = api.sdmm(X, prox_f, step_f, proxs_g=[prox_g, api.prox_plus], max_iter=100, e_rel=1e-5)
+    n, _ = api.iterations()
+    return {"X": X, "converged": np.bool_(conv), "iterations": np.int64(n)}
