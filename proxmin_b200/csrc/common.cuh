@@ -1,0 +1,76 @@
+// Shared internals of libproxmin_b200.so: context, error reporting, launch bookkeeping.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/proxmin_b200.h"
+
+void pmx_set_error(const char* fmt, ...);
+
+#define PMX_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      pmx_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));     \
+      return PMX_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define PMX_CHECK(st)                 \
+  do {                                \
+    int _s = (st);                    \
+    if (_s != PMX_OK) return _s;      \
+  } while (0)
+
+#define PMX_REQUIRE(cond, msg)                                        \
+  do {                                                                \
+    if (!(cond)) {                                                    \
+      pmx_set_error("%s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond); \
+      return PMX_ERR_ARG;                                             \
+    }                                                                 \
+  } while (0)
+
+// Device-side control block of a solver run.  Every solver kernel starts with
+// `if (ctl->done) return;` so that the iterate freezes at exactly the iteration where
+// the reference would `break` (algorithms.py:134-135) even though the host has already
+// enqueued further iterations.
+struct pmx_ctl {
+  int done;          // set when every block converged (or a non-finite step was met)
+  int it;            // iterations completed
+  int conv[2];       // convergence flags of the last completed iteration
+  int nonfinite;     // Gram matrix / lambda_max not finite
+  int sub_done;      // adaprox: proximal sub-iteration loop of the current block finished
+  int sub_tau;       // adaprox: sub-iterations used by the current block in this iteration
+  int sub_parity;    // adaprox: which z buffer holds the result
+  long long sub_total[2];
+  double norms[8];   // [0..2] block A: |dX|^2, |X|^2, |Xprev|^2 ; [3..5] block S ; [6] loss ; [7] spare
+  float step[2];     // 1/lambda_max for A and S (algorithms.py:106)
+  float lip[2];      // lambda_max(S S^T), lambda_max(A^T A)
+  float psi_max[2];  // adaprox: max(Psi) per block (algorithms.py:384)
+  float pad[2];
+};
+
+struct pmx_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;   // main stream: every kernel of the hot path
+  cudaStream_t aux;      // side stream: Gram / lambda_max overlap with the gradient kernel
+  cudaEvent_t ev_fork, ev_join, ev_t0, ev_t1;
+  long long launches;
+  // NCCL (dlopen'ed lazily)
+  void* nccl_comm;
+  int world, rank;
+  // scratch
+  int* h_flags;          // pinned host mirror for polled device flags
+  char dev_name[128];
+  size_t total_mem;
+};
+
+static inline int pmx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define PMX_LAUNCHED(ctx) ((ctx)->launches++)
+
+int pmx_check_launch(pmx_ctx* ctx, const char* what);

@@ -1,0 +1,458 @@
+// Elementwise / reduction kernels of the hot path (all HBM- or L2-bound):
+//   k_upd_flat / k_upd_cols / k_upd_rows : transform -> prox chain -> store -> norms
+//   k_extrapolate                         : Nesterov point  (algorithms.py:94-95)
+//   k_split_bf16                          : fp32 -> (hi, lo) bf16 operands for the tcgen05 GEMMs
+//   k_adaprox_moments                     : moment update + Phi/Psi step (algorithms.py:147-245, :378)
+// Grids are sized to a multiple of the SM count; loads are coalesced (thread index runs
+// along the contiguous dimension) and 128-bit where the layout allows.
+#include <cuda_bf16.h>
+
+#include "prox.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide reduction of three partial sums, then one double atomicAdd per block and value
+__device__ __forceinline__ void block_accumulate3(float a, float b, float c, double* out) {
+  __shared__ float red[3][32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[0][w] = a;
+    red[1][w] = b;
+    red[2][w] = c;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = lane < nw ? red[0][lane] : 0.f;
+    b = lane < nw ? red[1][lane] : 0.f;
+    c = lane < nw ? red[2][lane] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    if (lane == 0) {
+      atomicAdd(out + 0, (double)a);
+      atomicAdd(out + 1, (double)b);
+      atomicAdd(out + 2, (double)c);
+    }
+  }
+}
+
+__device__ __forceinline__ bool skip(const UpdIO& io) {
+  return (io.done && *io.done) || (io.done2 && *io.done2);
+}
+
+// the value the prox chain starts from, and the step handed to the chain
+template <int IN>
+__device__ __forceinline__ float transform(const UpdIO& io, size_t i, int r, int c, float& pstep) {
+  const float s = step_at(io.step, r, c);
+  if (IN == IN_PGM) {  // algorithms.py:108  _X[j] - T[j]*S[j]*G[j]
+    pstep = s;
+    return io.Xin[i] - s * io.G[i];
+  }
+  if (IN == IN_ADASUB) {  // algorithms.py:384,387  z - gamma/Alpha * Psi * (z - X), prox step gamma
+    const float gamma = s / io.psimax[0];
+    const float z = io.Xin[i];
+    pstep = gamma;
+    return z - gamma / s * io.G[i] * (z - io.X0[i]);
+  }
+  pstep = s;
+  return io.Xin[i];
+}
+
+// the step the prox chain sees (thresholds of type="relative"), for passes after the first
+template <int IN>
+__device__ __forceinline__ float prox_step(const UpdIO& io, int r, int c) {
+  const float s = step_at(io.step, r, c);
+  return (IN == IN_ADASUB) ? s / io.psimax[0] : s;
+}
+
+// ---- elementwise-only chains: one thread per element, grid-stride -----------------------
+template <int IN>
+__global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
+  if (skip(io)) return;
+  const size_t n = (size_t)io.rows * io.cols;
+  float nd = 0.f, nn = 0.f, np = 0.f;
+  const bool need_rc = io.step.mode >= 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = 0, c = 0;
+    if (need_rc) {
+      r = (int)(i / io.cols);
+      c = (int)(i - (size_t)r * io.cols);
+    }
+    const float prev = io.Xprev ? io.Xprev[i] : 0.f;
+    float ps;
+    float v = transform<IN>(io, i, r, c, ps);
+    v = chain_segment(ch, 0, ch.n, v, ps);
+    if (io.Xold_out) io.Xold_out[i] = prev;
+    io.Xout[i] = v;
+    const float d = v - prev;
+    nd += d * d;
+    nn += v * v;
+    np += prev * prev;
+  }
+  if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+}
+
+// ---- chains with UNITY(axis=0): one thread owns a column (coalesced across threads) -----
+template <int IN>
+__global__ void __launch_bounds__(kThreads) k_upd_cols(ProxChain ch, UpdIO io) {
+  if (skip(io)) return;
+  float nd = 0.f, nn = 0.f, np = 0.f;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < io.cols) {
+    const bool alias = (io.Xprev == io.Xout);
+    const float* prev_src = alias ? io.Xold_out : io.Xprev;
+    int a = 0, b = chain_next_unity(ch, 0);
+    // pass 0: transform + first elementwise segment; column sum in row order (NumPy's order for axis=0)
+    float sum = 0.f;
+    for (int r = 0; r < io.rows; ++r) {
+      const size_t i = (size_t)r * io.cols + c;
+      const float prev = io.Xprev ? io.Xprev[i] : 0.f;
+      float ps;
+      float v = transform<IN>(io, i, r, c, ps);
+      v = chain_segment(ch, a, b, v, ps);
+      if (io.Xold_out) io.Xold_out[i] = prev;
+      io.Xout[i] = v;
+      sum += v;
+      if (b >= ch.n) {
+        const float d = v - prev;
+        nd += d * d; nn += v * v; np += prev * prev;
+      }
+    }
+    // one further pass per UNITY op: divide by the column sum, then the next elementwise segment
+    while (b < ch.n) {
+      a = b + 1;
+      b = chain_next_unity(ch, a);
+      const float denom = sum;
+      sum = 0.f;
+      for (int r = 0; r < io.rows; ++r) {
+        const size_t i = (size_t)r * io.cols + c;
+        float v = io.Xout[i] / denom;                     // operators.py:44
+        v = chain_segment(ch, a, b, v, prox_step<IN>(io, r, c));
+        io.Xout[i] = v;
+        sum += v;
+        if (b >= ch.n) {
+          const float prev = prev_src ? prev_src[i] : 0.f;
+          const float d = v - prev;
+          nd += d * d; nn += v * v; np += prev * prev;
+        }
+      }
+    }
+  }
+  if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+}
+
+// ---- chains with UNITY(axis=1): one warp owns a row ------------------------------------
+template <int IN>
+__global__ void __launch_bounds__(kThreads) k_upd_rows(ProxChain ch, UpdIO io) {
+  if (skip(io)) return;
+  float nd = 0.f, nn = 0.f, np = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const bool alias = (io.Xprev == io.Xout);
+  const float* prev_src = alias ? io.Xold_out : io.Xprev;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < io.rows; r += gridDim.x * warps_per_block) {
+    int a = 0, b = chain_next_unity(ch, 0);
+    float sum = 0.f;
+    for (int c = lane; c < io.cols; c += 32) {
+      const size_t i = (size_t)r * io.cols + c;
+      const float prev = io.Xprev ? io.Xprev[i] : 0.f;
+      float ps;
+      float v = transform<IN>(io, i, r, c, ps);
+      v = chain_segment(ch, a, b, v, ps);
+      if (io.Xold_out) io.Xold_out[i] = prev;
+      io.Xout[i] = v;
+      sum += v;
+      if (b >= ch.n) {
+        const float d = v - prev;
+        nd += d * d; nn += v * v; np += prev * prev;
+      }
+    }
+    while (b < ch.n) {
+      a = b + 1;
+      b = chain_next_unity(ch, a);
+      const float denom = warp_sum(sum);
+      sum = 0.f;
+      for (int c = lane; c < io.cols; c += 32) {
+        const size_t i = (size_t)r * io.cols + c;
+        float v = io.Xout[i] / denom;
+        v = chain_segment(ch, a, b, v, prox_step<IN>(io, r, c));
+        io.Xout[i] = v;
+        sum += v;
+        if (b >= ch.n) {
+          const float prev = prev_src ? prev_src[i] : 0.f;
+          const float d = v - prev;
+          nd += d * d; nn += v * v; np += prev * prev;
+        }
+      }
+    }
+  }
+  if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+}
+
+template <int IN>
+int launch_update_t(pmx_ctx* ctx, const ProxChain& chain, const UpdIO& io) {
+  const int ax = chain_unity_axis(chain);
+  const size_t n = (size_t)io.rows * io.cols;
+  if (n == 0) return PMX_OK;
+  if (ax == 2) {
+    pmx_set_error("prox chain mixes UNITY along both axes; apply it as two chains");
+    return PMX_ERR_UNSUPPORTED;
+  }
+  if (ax >= 0 && io.norms && io.Xprev == io.Xout && !io.Xold_out) {
+    pmx_set_error("in-place UNITY update with norms needs an Xold buffer");
+    return PMX_ERR_ARG;
+  }
+  if (ax == -1) {
+    long long blocks = (long long)((n + kThreads - 1) / kThreads);
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_upd_flat<IN><<<(int)blocks, kThreads, 0, ctx->stream>>>(chain, io);
+  } else if (ax == 0) {
+    k_upd_cols<IN><<<pmx_div_up(io.cols, kThreads), kThreads, 0, ctx->stream>>>(chain, io);
+  } else {
+    const int wpb = kThreads / 32;
+    long long blocks = pmx_div_up(io.rows, wpb);
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_upd_rows<IN><<<(int)blocks, kThreads, 0, ctx->stream>>>(chain, io);
+  }
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "update kernel");
+}
+
+}  // namespace
+
+int launch_update(pmx_ctx* ctx, int in_kind, const ProxChain& chain, const UpdIO& io) {
+  switch (in_kind) {
+    case IN_PLAIN: return launch_update_t<IN_PLAIN>(ctx, chain, io);
+    case IN_PGM: return launch_update_t<IN_PGM>(ctx, chain, io);
+    case IN_ADASUB: return launch_update_t<IN_ADASUB>(ctx, chain, io);
+  }
+  pmx_set_error("bad transform kind %d", in_kind);
+  return PMX_ERR_ARG;
+}
+
+// =========================================================================================
+// zero fill that honours the device-side stop flag (a plain memset would wipe the "last
+// gradient" the solvers hand back after the loop froze, algorithms.py:144)
+// =========================================================================================
+__global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ p4, size_t n4, float* __restrict__ tail,
+                                                   int ntail, const int* done) {
+  if (done && *done) return;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
+int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done) {
+  if (n == 0) return PMX_OK;
+  const size_t n4 = n / 4;
+  long long blocks = (long long)((n4 + kThreads - 1) / kThreads);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_zero<<<(int)blocks, kThreads, 0, st>>>(reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4), done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_zero");
+}
+
+// =========================================================================================
+// Nesterov extrapolation  Xe = X + omega (X - Xold)   (algorithms.py:94-95)
+// =========================================================================================
+__global__ void __launch_bounds__(kThreads) k_extrapolate(const float* __restrict__ X, const float* __restrict__ Xold,
+                                                          float* __restrict__ Xe, size_t n, float omega,
+                                                          const int* done) {
+  if (done && *done) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = X[i];
+    Xe[i] = x + omega * (x - Xold[i]);
+  }
+}
+
+int launch_extrapolate(pmx_ctx* ctx, const float* X, const float* Xold, float* Xe, size_t n, float omega,
+                       const int* done) {
+  long long blocks = (long long)((n + kThreads - 1) / kThreads);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return PMX_OK;
+  k_extrapolate<<<(int)blocks, kThreads, 0, ctx->stream>>>(X, Xold, Xe, n, omega, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_extrapolate");
+}
+
+// =========================================================================================
+// fp32 -> (hi, lo) bf16 split, x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|.
+// The tcgen05 GEMMs compute hi*hi + hi*lo + lo*hi in fp32 (plain TF32/BF16 inputs
+// miss the 1e-4 parity target; the 3-term split clears it with margin).
+// Source is rows x cols (ld = cols); destination is rows_pad x ld_dst, zero padded.
+// =========================================================================================
+__global__ void __launch_bounds__(kThreads) k_split_bf16(const float* __restrict__ X, int rows, int cols,
+                                                         __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, int rows_pad, int ld_dst,
+                                                         const int* done) {
+  if (done && *done) return;
+  const size_t n = (size_t)rows_pad * ld_dst;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_dst);
+    const int c = (int)(i - (size_t)r * ld_dst);
+    float x = 0.f;
+    if (r < rows && c < cols) x = X[(size_t)r * cols + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int launch_split_bf16(pmx_ctx* ctx, const float* X, int rows, int cols, void* hi, void* lo, int rows_pad, int ld_dst,
+                      const int* done) {
+  const size_t n = (size_t)rows_pad * ld_dst;
+  long long blocks = (long long)((n + kThreads - 1) / kThreads);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return PMX_OK;
+  k_split_bf16<<<(int)blocks, kThreads, 0, ctx->stream>>>(X, rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                          rows_pad, ld_dst, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_split_bf16");
+}
+
+// =========================================================================================
+// adaprox moment update (algorithms.py:147-245) fused with the step X -= Alpha*Phi/Psi (:378),
+// the copy z = X (:383) and the block-wide max(Psi) (:384).
+// =========================================================================================
+struct AdaArgs {
+  const float* G;
+  float* M;
+  float* V;
+  float* Vhat;   // may be null (quirk: then the running max is never applied, algorithms.py:176-177)
+  float* X;
+  float* Psi;    // out
+  float* Z;      // out: copy of the stepped X
+  float* Xold;   // optional out: X before the step (convergence test, algorithms.py:371-372)
+  float* psimax; // out (atomicMax on the bit pattern; Psi >= 0)
+  const int* done;
+  size_t n;
+  int rows, cols;
+  StepSpec alpha;
+  int scheme;
+  double b1, b1_prev;  // b1 is a float64 array in the reference (algorithms.py:327-328): M is formed in double
+  float b2, eps, p;
+  int t;  // it + 1
+};
+
+__global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
+  if (a.done && *a.done) return;
+  float pm = 0.f;
+  // scalar recipe pieces, evaluated in fp32 like NumPy does for fp32 arrays with Python scalars
+  const double c1 = 1.0 - pow(a.b1, (double)a.t);                   // 1 - b1[it]**t  (np.float64 scalar)
+  const float c2 = (float)(1.0 - pow((double)a.b2, (double)a.t));   // 1 - b2**t      (Python float -> weak fp32)
+  const float omb2 = (float)(1.0 - (double)a.b2);
+  float radam_r = 0.f;
+  bool radam_rect = false;
+  if (a.scheme == PMX_RADAM) {  // algorithms.py:222-239 (scalar part, double like Python floats)
+    const double b2 = a.b2, tt = a.t;
+    const double rho_inf = 2.0 / (1.0 - b2) - 1.0;
+    const double rho = rho_inf - 2.0 * tt * pow(b2, tt) / (1.0 - pow(b2, tt));
+    radam_rect = rho > 4.0;
+    if (radam_rect) radam_r = (float)sqrt((rho - 4.0) * (rho - 2.0) * rho_inf / (rho_inf - 4.0) / (rho_inf - 2.0) / rho);
+  }
+  const bool need_rc = a.alpha.mode >= 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = 0, c = 0;
+    if (need_rc) {
+      r = (int)(i / a.cols);
+      c = (int)(i - (size_t)r * a.cols);
+    }
+    const float g = a.G[i];
+    const float m = (float)((1.0 - a.b1) * (double)g + a.b1 * (double)a.M[i]);
+    const float v = omb2 * (g * g) + a.b2 * a.V[i];
+    a.M[i] = m;
+    a.V[i] = v;
+    double phi;  // Phi is float64 in the reference whenever b1[it] enters it
+    float psi;
+    switch (a.scheme) {
+      case PMX_ADAM:
+        phi = (double)m / c1;
+        psi = sqrtf(v / c2) + a.eps;
+        break;
+      case PMX_NADAM:
+        phi = (a.b1 * (double)m + (1.0 - a.b1) * (double)g) / c1;
+        psi = sqrtf(v / c2) + a.eps;
+        break;
+      case PMX_RADAM:
+        phi = (double)m / c1;
+        psi = radam_rect ? sqrtf(v / c2) / radam_r : 1.0f;
+        if (a.eps > 0.f) psi = fmaxf(psi, sqrtf(a.eps));
+        break;
+      default: {  // AMSGRAD / PADAM / ADAMX
+        float vh = v;
+        if (a.Vhat) {
+          float old = a.Vhat[i];
+          if (a.scheme == PMX_ADAMX) {
+            const double f = ((1.0 - a.b1) * (1.0 - a.b1)) / ((1.0 - a.b1_prev) * (1.0 - a.b1_prev));
+            old = (float)(f * (double)old);
+          }
+          vh = fmaxf(old, v);
+          a.Vhat[i] = vh;
+        }
+        if (a.eps > 0.f) vh = fmaxf(vh, a.eps);
+        phi = m;
+        psi = (a.scheme == PMX_PADAM) ? powf(vh, a.p) : sqrtf(vh);
+      }
+    }
+    const float al = step_at(a.alpha, r, c);
+    const float xo = a.X[i];
+    float xn;  // algorithms.py:378
+    if (a.scheme == PMX_ADAM || a.scheme == PMX_NADAM || a.scheme == PMX_RADAM)
+      xn = (float)((double)xo - (double)al * phi / (double)psi);
+    else
+      xn = xo - al * (float)phi / psi;
+    if (a.Xold) a.Xold[i] = xo;
+    a.X[i] = xn;
+    a.Z[i] = xn;
+    a.Psi[i] = psi;
+    pm = fmaxf(pm, psi);
+    if (psi != psi) pm = psi;  // np.max propagates NaN
+  }
+  // block max -> global
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, pm, o);
+    pm = (pm != pm || other != other) ? (pm + other) : fmaxf(pm, other);
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m2 = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) {
+      const float o2 = red[w];
+      m2 = (m2 != m2 || o2 != o2) ? (m2 + o2) : fmaxf(m2, o2);
+    }
+    // Psi >= 0 (or NaN, whose bit pattern 0x7fc00000 compares above every finite float)
+    atomicMax((int*)a.psimax, __float_as_int(m2));
+  }
+}
+
+int launch_adaprox_moments(pmx_ctx* ctx, const AdaArgs& a) {
+  long long blocks = (long long)((a.n + kThreads - 1) / kThreads);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return PMX_OK;
+  k_adaprox_moments<<<(int)blocks, kThreads, 0, ctx->stream>>>(a);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_adaprox_moments");
+}

@@ -1,0 +1,537 @@
+// Fused NMF gradient kernel for sm_100a: one pass over Y computes
+//     R = A S - Y,   G_A = R S^T,   G_S = A^T R,   loss = |R|^2 / 2          (nmf.py:13-41)
+// with tcgen05 tensor-core MMAs (TMEM accumulators), TMA loads, and warp-specialised roles.
+//
+// Precision: every GEMM is the 3-term BF16 split  hi*hi + hi*lo + lo*hi  with fp32 accumulation
+// (x = hi + lo, |x - hi - lo| <= 2^-17 |x|).  SURVEY 7.3 measured that single-pass TF32/BF16
+// operands miss the 1e-4 parity target by 10-100x while this split clears it with margin.
+// A and S arrive pre-split (k_split_bf16); R is split in the epilogue registers.
+//
+// Tiling: a tile is 128 rows (m) x 128 columns (n) of Y; K <= 64 (operands zero-padded to 64).
+// The tile sequence is stripe-major (all m-blocks of a 128-column stripe are consecutive) and is
+// cut into gridDim.x contiguous, equally long ranges -- one persistent CTA per SM -- so the load is
+// balanced to within one tile.  Inside a stripe segment G_S^T accumulates in TMEM across the
+// m-blocks; the 128 x 64 G_A partial of every tile is flushed with vector red.add into the
+// (L2-resident) G_A buffer.
+//
+// Shared memory (all operands are "panels": rows of 128 bytes, 128B-swizzled in 8-row atoms, which
+// the same bytes can be read as a K-major or an MN-major UMMA operand):
+//   S_hi,S_lo  [2 n-panels][64 k-rows][128B]   32 KB   per stripe        (TMA)
+//   A_hi,A_lo  [128 m-rows][128B] x 2 slots    64 KB   per tile          (TMA)
+//   R_hi,R_lo  [2 n-panels][128 m-rows][128B]  64 KB   per tile          (epilogue writes)
+//   Y ring     4 x [128 m-rows][32 fp32]       64 KB   4 sub-tiles/tile  (TMA)
+// TMEM (512 columns): residual accumulator 2 x 128, G_A accumulator 2 x 64, G_S^T accumulator 64.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM -> registers -> residual -> SMEM, gradient flushes).
+#include <cuda_bf16.h>
+
+#include "grad_umma.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TILE_M = 128, TILE_N = 128, KP = 64;
+constexpr int Y_SUB = 32;           // columns per Y sub-tile (128 bytes of fp32)
+constexpr int Y_STAGES = 4;
+constexpr uint32_t PANEL_S = 64 * 128;    // bytes of one S panel (64 k-rows)
+constexpr uint32_t PANEL_R = 128 * 128;   // bytes of one R / A panel (128 m-rows)
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t OFF_S_HI = 0;
+constexpr uint32_t OFF_S_LO = OFF_S_HI + 2 * PANEL_S;
+constexpr uint32_t OFF_A = OFF_S_LO + 2 * PANEL_S;          // slot s: hi at OFF_A + s*2*PANEL_R, lo right after
+constexpr uint32_t OFF_R_HI = OFF_A + 4 * PANEL_R;
+constexpr uint32_t OFF_R_LO = OFF_R_HI + 2 * PANEL_R;
+constexpr uint32_t OFF_Y = OFF_R_LO + 2 * PANEL_R;
+constexpr uint32_t OFF_BAR = OFF_Y + Y_STAGES * PANEL_R;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
+
+enum {  // mbarrier indices
+  B_S_FULL = 0, B_S_EMPTY, B_A_FULL, B_A_EMPTY = B_A_FULL + 2, B_Y_FULL = B_A_EMPTY + 2,
+  B_Y_EMPTY = B_Y_FULL + Y_STAGES, B_ACC_FULL = B_Y_EMPTY + Y_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2,
+  B_R_FULL = B_ACC_EMPTY + 2, B_R_EMPTY, B_GA_FULL, B_GA_EMPTY = B_GA_FULL + 2, B_GS_FULL = B_GA_EMPTY + 2,
+  B_GS_EMPTY, B_COUNT
+};
+
+constexpr uint32_t TM_ACC = 0, TM_GA = 256, TM_GS = 384;   // TMEM column offsets
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate), M x N x 16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor layout, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Params {
+  int M, N, K;
+  int MB;                 // m-blocks per stripe
+  long long total_tiles;  // stripes * MB
+  float* GA;
+  float* GS;
+  double* loss;
+  const int* done;
+};
+
+__global__ void __launch_bounds__(256, 1)
+k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAhi,
+            const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmShi,
+            const __grid_constant__ CUtensorMap tmSlo, Params p) {
+  if (p.done && *p.done) return;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + OFF_BAR + 8 * B_COUNT);
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const long long g_begin = (long long)blockIdx.x * p.total_tiles / gridDim.x;
+  const long long g_end = (long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B_COUNT; ++i) {
+      uint32_t count = 1;
+      if (i >= B_Y_EMPTY && i < B_Y_EMPTY + Y_STAGES) count = 4;
+      if (i == B_ACC_EMPTY || i == B_ACC_EMPTY + 1) count = 4;
+      if (i == B_R_FULL) count = 4;
+      if (i == B_GA_EMPTY || i == B_GA_EMPTY + 1) count = 4;
+      if (i == B_GS_EMPTY) count = 4;
+      mbar_init(bar(i), count);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto first_in_seg = [&](long long g) { return g == g_begin || (g % p.MB) == 0; };
+  auto last_in_seg = [&](long long g) { return g == g_end - 1 || (g % p.MB) == p.MB - 1; };
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t t = 0, seg = 0;
+      for (long long g = g_begin; g < g_end; ++g, ++t) {
+        const int stripe = (int)(g / p.MB), mb = (int)(g % p.MB);
+        const int m0 = mb * TILE_M, n0 = stripe * TILE_N;
+        const uint32_t slot = t & 1;
+        // A tile (hi, lo): 2 x 16 KB
+        mbar_wait(bar(B_A_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(B_A_FULL + slot), 2 * PANEL_R);
+        tma_load_2d(base + OFF_A + slot * 2 * PANEL_R, &tmAhi, 0, m0, bar(B_A_FULL + slot));
+        tma_load_2d(base + OFF_A + slot * 2 * PANEL_R + PANEL_R, &tmAlo, 0, m0, bar(B_A_FULL + slot));
+        // Y sub-tiles
+        for (int q = 0; q < 4; ++q) {
+          mbar_wait(bar(B_Y_EMPTY + q), (t & 1) ^ 1);
+          mbar_expect_tx(bar(B_Y_FULL + q), PANEL_R);
+          tma_load_2d(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q));
+        }
+        // S stripe (after the prefetch of this tile's A and Y so that the stripe switch does not stall them)
+        if (first_in_seg(g)) {
+          mbar_wait(bar(B_S_EMPTY), (seg & 1) ^ 1);
+          mbar_expect_tx(bar(B_S_FULL), 4 * PANEL_S);
+          tma_load_2d(base + OFF_S_HI, &tmShi, n0, 0, bar(B_S_FULL));
+          tma_load_2d(base + OFF_S_HI + PANEL_S, &tmShi, n0 + 64, 0, bar(B_S_FULL));
+          tma_load_2d(base + OFF_S_LO, &tmSlo, n0, 0, bar(B_S_FULL));
+          tma_load_2d(base + OFF_S_LO + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL));
+          ++seg;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);  // A tile K-major, S tile MN-major
+      constexpr uint32_t ID_GA = make_idesc(128, 64, 0, 0);    // R K-major, S tile K-major
+      constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);    // R^T (MN-major), A tile MN-major
+      uint32_t seg_full = 0;  // S segments consumed so far (parity source for s_full)
+
+      auto issue_residual = [&](long long g, uint32_t t) {
+        const uint32_t slot = t & 1;
+        mbar_wait(bar(B_A_FULL + slot), (t >> 1) & 1);
+        if (first_in_seg(g)) {
+          mbar_wait(bar(B_S_FULL), seg_full & 1);
+          ++seg_full;
+        }
+        mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_hi = base + OFF_A + slot * 2 * PANEL_R, a_lo = a_hi + PANEL_R;
+        const uint32_t d = tmem + TM_ACC + slot * 128;
+        // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16)
+        const uint32_t a_src[3] = {a_hi, a_hi, a_lo};
+        const uint32_t s_src[3] = {base + OFF_S_HI, base + OFF_S_LO, base + OFF_S_HI};
+#pragma unroll
+        for (int term = 0; term < 3; ++term)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major
+            const uint64_t bd = make_desc(s_src[term] + ks * 2048, PANEL_S, 1024);      // MN-major: LBO = next 64 n
+            umma_bf16(d, ad, bd, ID_RES, (term | ks) ? 1u : 0u);
+          }
+        tc_commit(bar(B_ACC_FULL + slot));
+      };
+
+      uint32_t t = 0, seg = 0;
+      if (g_begin < g_end) issue_residual(g_begin, 0);
+      for (long long g = g_begin; g < g_end; ++g, ++t) {
+        const bool has_next = g + 1 < g_end;
+        if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a stripe
+        const uint32_t slot = t & 1;
+        mbar_wait(bar(B_R_FULL), t & 1);
+        mbar_wait(bar(B_GA_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        const bool first = first_in_seg(g);
+        if (first) mbar_wait(bar(B_GS_EMPTY), (seg & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_hi = base + OFF_A + slot * 2 * PANEL_R, a_lo = a_hi + PANEL_R;
+        const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
+        const uint32_t s_hi = base + OFF_S_HI, s_lo = base + OFF_S_LO;
+        {  // G_A[m, k] = R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps)
+          const uint32_t d = tmem + TM_GA + slot * 64;
+          const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
+          const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = make_desc(r_src[term] + (ks >> 2) * PANEL_R + (ks & 3) * 32, 16, 1024);  // K-major
+              const uint64_t bd = make_desc(s_src[term] + (ks >> 2) * PANEL_S + (ks & 3) * 32, 16, 1024);  // K-major
+              umma_bf16(d, ad, bd, ID_GA, (term | ks) ? 1u : 0u);
+            }
+        }
+        {  // G_S^T[n, k] += R^T A : M = n (128), N = k (64), K = m (128: 8 k-steps)
+          const uint32_t d = tmem + TM_GS;
+          const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
+          const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = make_desc(r_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major: LBO = next 64 n
+              const uint64_t bd = make_desc(a_src[term] + ks * 2048, 1024, 1024);     // MN-major, one 64-wide atom
+              umma_bf16(d, ad, bd, ID_GS, (!first || (term | ks)) ? 1u : 0u);
+            }
+        }
+        tc_commit(bar(B_R_EMPTY));
+        tc_commit(bar(B_A_EMPTY + slot));
+        tc_commit(bar(B_GA_FULL + slot));
+        if (last_in_seg(g)) {
+          tc_commit(bar(B_GS_FULL));
+          tc_commit(bar(B_S_EMPTY));
+          ++seg;
+        }
+        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new stripe: needs the new S tile
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q4 * 32 + lane;          // row of the tile (m for acc / G_A, n for G_S^T)
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    float loss_part = 0.f;
+    uint32_t t = 0, seg = 0;
+    long long pending_g = -1;   // tile whose G_A accumulator still has to be flushed
+    uint32_t pending_t = 0;
+
+    auto flush_ga = [&](long long g, uint32_t tt) {
+      const uint32_t slot = tt & 1;
+      const int m = (int)(g % p.MB) * TILE_M + row;
+      mbar_wait(bar(B_GA_FULL + slot), (tt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + TM_GA + slot * 64 + half * 32, v);
+        tmem_ld_wait();
+        if (m < p.M) {
+          float* dst = p.GA + (size_t)m * p.K + half * 32;
+          if ((p.K & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              if (half * 32 + k < p.K)
+                red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                           __uint_as_float(v[k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (half * 32 + k < p.K) atomicAdd(dst + k, __uint_as_float(v[k]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_GA_EMPTY + slot));
+    };
+
+    for (long long g = g_begin; g < g_end; ++g, ++t) {
+      const uint32_t slot = t & 1;
+      mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
+      mbar_wait(bar(B_R_EMPTY), (t & 1) ^ 1);   // MMAs of the previous tile no longer read R
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        mbar_wait(bar(B_Y_FULL + q), t & 1);
+        uint32_t acc[32];
+        tmem_ld32(lane_addr + TM_ACC + slot * 128 + q * 32, acc);
+        // this row of the Y sub-tile: 8 x 16-byte chunks, 128B-swizzled by TMA
+        const uint8_t* yrow = base_ptr + OFF_Y + q * PANEL_R + row * 128;
+        float4 yv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) yv[c] = *reinterpret_cast<const float4*>(yrow + ((c ^ (row & 7)) << 4));
+        tmem_ld_wait();
+        const float* yf = reinterpret_cast<const float*>(yv);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float r0 = __uint_as_float(acc[j]) - yf[j];          // nmf.py:40  (A S - Y)
+          const float r1 = __uint_as_float(acc[j + 1]) - yf[j + 1];
+          loss_part = fmaf(r0, r0, loss_part);
+          loss_part = fmaf(r1, r1, loss_part);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
+          const float2 hf = __bfloat1622float2(h);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - hf.x, r1 - hf.y);
+          hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        // R_hi / R_lo: panel q/2, chunks (q&1)*4 .. +3 of this row
+        uint8_t* rh = base_ptr + OFF_R_HI + (q >> 1) * PANEL_R + row * 128;
+        uint8_t* rl = base_ptr + OFF_R_LO + (q >> 1) * PANEL_R + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = ((q & 1) * 4 + c) ^ (row & 7);
+          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+          *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));
+      }
+      tc_fence_before();
+      fence_async_smem();   // generic-proxy writes of R -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(B_ACC_EMPTY + slot));
+        mbar_arrive(bar(B_R_FULL));
+      }
+      // deferred flush of the previous tile's G_A (its MMAs finished while we built this R)
+      if (pending_g >= 0) flush_ga(pending_g, pending_t);
+      pending_g = g;
+      pending_t = t;
+      if (last_in_seg(g)) {
+        flush_ga(g, t);  // waits for this tile's MMAs
+        pending_g = -1;
+        // G_S^T[n, k] -> G_S[k, n]: coalesced along n across the warp
+        mbar_wait(bar(B_GS_FULL), seg & 1);
+        tc_fence_after();
+        const int n = (int)(g / p.MB) * TILE_N + row;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + TM_GS + half * 32, v);
+          tmem_ld_wait();
+          if (n < p.N) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (half * 32 + k < p.K) atomicAdd(p.GS + (size_t)(half * 32 + k) * p.N + n, __uint_as_float(v[k]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_GS_EMPTY));
+        ++seg;
+      }
+    }
+    if (p.loss) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+      if (lane == 0) atomicAdd(p.loss, 0.5 * (double)loss_part);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows,
+             uint64_t pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pmx_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return PMX_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  (void)elem_bytes;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pmx_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PMX_ERR_CUDA;
+  }
+  return PMX_OK;
+}
+
+}  // namespace
+
+struct UmmaPlan {
+  int M, N, K, Mp, Np;
+  void *Ahi, *Alo, *Shi, *Slo;  // bf16 operand buffers (zero padded)
+  CUtensorMap tmY, tmAhi, tmAlo, tmShi, tmSlo;
+};
+
+bool umma_supported(int M, int N, int K) { return K >= 1 && K <= KP && M >= 1 && N >= 1; }
+
+int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out) {
+  PMX_REQUIRE(umma_supported(M, N, K), "unsupported shape for the tcgen05 kernel");
+  PMX_REQUIRE((ldY % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) % 16) == 0, "Y must be 16-byte aligned with a pitch multiple of 4");
+  UmmaPlan* pl = new UmmaPlan();
+  memset(pl, 0, sizeof(*pl));
+  pl->M = M; pl->N = N; pl->K = K;
+  pl->Mp = pmx_div_up(M, TILE_M) * TILE_M;
+  pl->Np = pmx_div_up(N, TILE_N) * TILE_N;
+  PMX_CUDA(cudaSetDevice(ctx->device));
+  PMX_CUDA(cudaMalloc(&pl->Ahi, (size_t)pl->Mp * KP * 2));
+  PMX_CUDA(cudaMalloc(&pl->Alo, (size_t)pl->Mp * KP * 2));
+  PMX_CUDA(cudaMalloc(&pl->Shi, (size_t)KP * pl->Np * 2));
+  PMX_CUDA(cudaMalloc(&pl->Slo, (size_t)KP * pl->Np * 2));
+  // Y: fp32, box 32 columns x 128 rows; out-of-bounds rows/columns are zero-filled by TMA
+  PMX_CHECK(make_map(&pl->tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldY * 4, Y_SUB, TILE_M));
+  PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, KP, (uint64_t)pl->Mp, KP * 2, KP, TILE_M));
+  PMX_CHECK(make_map(&pl->tmAlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Alo, KP, (uint64_t)pl->Mp, KP * 2, KP, TILE_M));
+  PMX_CHECK(make_map(&pl->tmShi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Shi, (uint64_t)pl->Np, KP, (uint64_t)pl->Np * 2, 64, KP));
+  PMX_CHECK(make_map(&pl->tmSlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Slo, (uint64_t)pl->Np, KP, (uint64_t)pl->Np * 2, 64, KP));
+  static bool attr = false;
+  if (!attr) {
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr = true;
+  }
+  *out = pl;
+  return PMX_OK;
+}
+
+void umma_plan_destroy(UmmaPlan* pl) {
+  if (!pl) return;
+  cudaFree(pl->Ahi);
+  cudaFree(pl->Alo);
+  cudaFree(pl->Shi);
+  cudaFree(pl->Slo);
+  delete pl;
+}
+
+int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S, float* GA, float* GS, double* loss,
+                     const int* done) {
+  PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
+  PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
+  PMX_CHECK(launch_zero(ctx, ctx->stream, GA, (size_t)pl->M * pl->K, done));
+  PMX_CHECK(launch_zero(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, done));
+  if (loss) PMX_CHECK(launch_zero(ctx, ctx->stream, reinterpret_cast<float*>(loss), 2, done));
+  Params p;
+  p.M = pl->M; p.N = pl->N; p.K = pl->K;
+  p.MB = pl->Mp / TILE_M;
+  p.total_tiles = (long long)(pl->Np / TILE_N) * p.MB;
+  p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
+  int grid = (int)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
+  k_grad_umma<<<grid, 256, SMEM_BYTES, ctx->stream>>>(pl->tmY, pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_grad_umma");
+}

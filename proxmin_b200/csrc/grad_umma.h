@@ -1,0 +1,13 @@
+// tcgen05 / TMA / TMEM gradient kernel (grad_umma.cu): host-side plan and launch wrapper.
+#pragma once
+#include "common.cuh"
+
+struct UmmaPlan;
+
+// shapes the tcgen05 kernel takes: K <= 64 (operands are zero-padded to K = 64), any M, any N
+bool umma_supported(int M, int N, int K);
+// Y must be 16-byte aligned with a row pitch (ldY floats) that is a multiple of 4
+int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out);
+void umma_plan_destroy(UmmaPlan* plan);
+int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* plan, const float* A, const float* S, float* GA, float* GS, double* loss,
+                     const int* done);

@@ -1,0 +1,286 @@
+// Lipschitz constants of the NMF gradient (nmf.py:44-49 step_A/step_S, utils.py:14-35
+// get_spectral_norm dense branch): lambda_max of the K x K Gram matrices S S^T and A^T A.
+//
+//   k_gram<TALL>   : Gram += X^T X (tall M x K operand) or X X^T (wide K x N operand), fp32 tiles in
+//                    shared memory, 4x4 register blocks, persistent blocks, one fp64 atomic flush per block.
+//   k_lambda_max   : one CTA per Gram: repeated squaring (B <- B^2 / trace) drives B to v1 v1^T for any
+//                    spectral gap, two fp64 power steps and a Rayleigh quotient with the ORIGINAL Gram give
+//                    lambda_max to ~1e-7 relative -- the accuracy LAPACK geev gives the reference in fp32.
+//                    Writes lip / step = 1/lip into the control block; flags non-finite input
+//                    (reference: numpy.linalg.LinAlgError from eigvals, utils.py:34).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxK = 128;
+constexpr int kTileLen = 32;  // rows (tall) / columns (wide) staged per step
+
+// acc[4][4] += sum_l T[l][i0..i0+3] * T[l][j0..j0+3]
+__device__ __forceinline__ void gram_block(const float* T, int len, int ldt, int i0, int j0, float acc[4][4]) {
+  for (int l = 0; l < len; ++l) {
+    const float* row = T + (size_t)l * ldt;
+    const float4 a = *reinterpret_cast<const float4*>(row + i0);
+    const float4 b = *reinterpret_cast<const float4*>(row + j0);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+  }
+}
+
+// X is rows x cols row-major.  TALL: Gram (cols x cols) over rows.  !TALL: Gram (rows x rows) over cols.
+template <bool TALL>
+__global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int rows, int cols, double* __restrict__ gram,
+                                              const int* done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) float smem[];
+  const int C = TALL ? cols : rows;        // Gram dimension
+  const long long L = TALL ? rows : cols;  // contraction length
+  const int C4 = (C + 3) & ~3;
+  const int ldt = C4 + 4;                  // padded row of the staged tile
+  float* T = smem;                         // [kTileLen][ldt]
+  const int nt = C4 / 4;
+  const int ntiles = nt * nt;
+  // each thread owns up to 4 register blocks (C <= 128 -> at most 1024 blocks for 256 threads)
+  float acc[4][4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[u][p][q] = 0.f;
+
+  const long long nchunks = (L + kTileLen - 1) / kTileLen;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long l0 = ch * kTileLen;
+    const int len = (int)min((long long)kTileLen, L - l0);
+    __syncthreads();
+    if (TALL) {  // rows l0..l0+len of X, contiguous in memory
+      for (int idx = threadIdx.x; idx < kTileLen * C4; idx += blockDim.x) {
+        const int l = idx / C4, c = idx - l * C4;
+        T[l * ldt + c] = (l < len && c < C) ? X[(size_t)(l0 + l) * cols + c] : 0.f;
+      }
+    } else {  // columns l0..l0+len of every row: coalesced along the column index
+      for (int idx = threadIdx.x; idx < kTileLen * C4; idx += blockDim.x) {
+        const int c = idx / kTileLen, l = idx - c * kTileLen;
+        T[l * ldt + c] = (l < len && c < C) ? X[(size_t)c * cols + (l0 + l)] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tile = threadIdx.x + u * 256;
+      if (tile < ntiles) gram_block(T, len, ldt, (tile / nt) * 4, (tile % nt) * 4, acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int tile = threadIdx.x + u * 256;
+    if (tile < ntiles) {
+      const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i0 + p < C && j0 + q < C) atomicAdd(&gram[(size_t)(i0 + p) * C + (j0 + q)], (double)acc[u][p][q]);
+    }
+  }
+}
+
+// One CTA (1024 threads).  gram: C x C fp64 (symmetric PSD).  which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].
+__global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ gram, int C, pmx_ctl* ctl, int which,
+                                                     int squarings) {
+  if (ctl->done) return;
+  extern __shared__ __align__(16) float smem[];
+  const int C4 = (C + 3) & ~3;
+  const int ldt = C4 + 4;
+  float* B0 = smem;                        // [C4][ldt]
+  float* B1 = B0 + (size_t)C4 * ldt;       // [C4][ldt]
+  double* v = reinterpret_cast<double*>(B1 + (size_t)C4 * ldt);  // [C4]
+  double* w = v + C4;                                             // [C4]
+  __shared__ double s_red[32];
+  __shared__ double s_scalar;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+
+  // load, detect non-finite entries, trace
+  double tr = 0.0;
+  for (int idx = tid; idx < C4 * C4; idx += blockDim.x) {
+    const int i = idx / C4, j = idx - i * C4;
+    double g = (i < C && j < C) ? gram[(size_t)i * C + j] : 0.0;
+    if (!isfinite(g)) s_bad = 1;
+    if (i == j) tr += g;
+    B0[i * ldt + j] = (float)g;
+  }
+  // block sum of tr
+  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = tr;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+    s_scalar = t;
+  }
+  __syncthreads();
+  const double trace0 = s_scalar;
+  if (s_bad || !isfinite(trace0)) {
+    if (tid == 0) {
+      ctl->nonfinite = 1;
+      ctl->done = 1;
+      ctl->lip[which] = __int_as_float(0x7fc00000);
+      ctl->step[which] = __int_as_float(0x7fc00000);
+    }
+    return;
+  }
+  if (trace0 <= 0.0) {  // zero matrix: lambda_max = 0, step = 1/0 = inf (the reference divides by zero too)
+    if (tid == 0) {
+      ctl->lip[which] = 0.f;
+      ctl->step[which] = __int_as_float(0x7f800000);
+    }
+    return;
+  }
+  // normalise by the trace so every power keeps entries in (0, 1]
+  {
+    const float inv = (float)(1.0 / trace0);
+    for (int idx = tid; idx < C4 * ldt; idx += blockDim.x) B0[idx] *= inv;
+  }
+  __syncthreads();
+
+  const int nt = C4 / 4;
+  const int ntiles = nt * nt;
+  float* cur = B0;
+  float* nxt = B1;
+  for (int s = 0; s < squarings; ++s) {
+    // nxt = cur^T cur = cur^2 (symmetric)
+    float tr_part = 0.f;
+    for (int tile = tid; tile < ntiles; tile += blockDim.x) {
+      const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
+      gram_block(cur, C4, ldt, i0, j0, acc);
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          nxt[(i0 + p) * ldt + j0 + q] = acc[p][q];
+          if (i0 + p == j0 + q) tr_part += acc[p][q];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) tr_part += __shfl_xor_sync(0xffffffffu, tr_part, o);
+    __syncthreads();  // everybody finished reading cur / s_red from the previous round
+    if ((tid & 31) == 0) s_red[tid >> 5] = (double)tr_part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+      s_scalar = t;
+    }
+    __syncthreads();
+    const float inv = (float)(1.0 / s_scalar);
+    for (int idx = tid; idx < C4 * ldt; idx += blockDim.x) nxt[idx] *= inv;
+    __syncthreads();
+    float* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  // v = column of the (near rank-one) power with the largest diagonal entry
+  if (tid == 0) {
+    int best = 0;
+    float bd = -1.f;
+    for (int i = 0; i < C; ++i)
+      if (cur[i * ldt + i] > bd) {
+        bd = cur[i * ldt + i];
+        best = i;
+      }
+    s_bad = best;
+  }
+  __syncthreads();
+  const int col = s_bad;
+  for (int i = tid; i < C4; i += blockDim.x) v[i] = (i < C) ? (double)cur[i * ldt + col] : 0.0;
+  __syncthreads();
+  // two fp64 power steps with the original Gram, then the Rayleigh quotient
+  for (int rep = 0; rep < 3; ++rep) {
+    for (int i = tid; i < C; i += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < C; ++j) acc += gram[(size_t)i * C + j] * v[j];
+      w[i] = acc;
+    }
+    __syncthreads();
+    if (rep == 2) break;
+    if (tid == 0) {
+      double nn = 0;
+      for (int i = 0; i < C; ++i) nn += w[i] * w[i];
+      s_scalar = nn > 0 ? 1.0 / sqrt(nn) : 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) v[i] = w[i] * s_scalar;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double num = 0, den = 0;
+    for (int i = 0; i < C; ++i) {
+      num += v[i] * w[i];
+      den += v[i] * v[i];
+    }
+    const double lam = den > 0 ? num / den : 0.0;
+    const float lf = (float)lam;             // the reference's eigvals runs in fp32 for fp32 inputs
+    ctl->lip[which] = lf;
+    ctl->step[which] = 1.0f / lf;            // nmf.py:45,49
+  }
+}
+
+}  // namespace
+
+int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int cols, bool tall, double* gram,
+                const int* done) {
+  const int C = tall ? cols : rows;
+  if (C > kMaxK) {
+    pmx_set_error("Gram dimension K=%d exceeds the supported maximum %d", C, kMaxK);
+    return PMX_ERR_UNSUPPORTED;
+  }
+  const long long L = tall ? rows : cols;
+  const int C4 = (C + 3) & ~3;
+  const size_t smem = (size_t)kTileLen * (C4 + 4) * sizeof(float);
+  long long nchunks = (L + kTileLen - 1) / kTileLen;
+  int blocks = (int)(nchunks < (long long)ctx->sm_count * 2 ? nchunks : (long long)ctx->sm_count * 2);
+  if (blocks < 1) blocks = 1;
+  cudaError_t e = cudaMemsetAsync(gram, 0, sizeof(double) * C * C, st);
+  if (e != cudaSuccess) {
+    pmx_set_error("memset gram: %s", cudaGetErrorString(e));
+    return PMX_ERR_CUDA;
+  }
+  if (tall)
+    k_gram<true><<<blocks, 256, smem, st>>>(X, rows, cols, gram, done);
+  else
+    k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, gram, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_gram");
+}
+
+int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which) {
+  if (C > kMaxK) {
+    pmx_set_error("Gram dimension K=%d exceeds the supported maximum %d", C, kMaxK);
+    return PMX_ERR_UNSUPPORTED;
+  }
+  const int C4 = (C + 3) & ~3;
+  const size_t smem = 2 * (size_t)C4 * (C4 + 4) * sizeof(float) + 2 * (size_t)C4 * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_lambda_max, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      pmx_set_error("cudaFuncSetAttribute(k_lambda_max): %s", cudaGetErrorString(e));
+      return PMX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  k_lambda_max<<<1, 1024, smem, st>>>(gram, C, ctl, which, 16);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_lambda_max");
+}

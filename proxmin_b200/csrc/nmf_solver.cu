@@ -1,0 +1,387 @@
+// NMF solver object: device-resident state and the iteration loops of
+//   algorithms.py:87-135 (pgm), :365-410 (adaprox), :800-844 (bsdmm via nmf.py:178-203)
+// specialised to the Gaussian-likelihood NMF objective of nmf.py:13-41.
+//
+// One iteration is a short, fixed sequence of kernels on the context's stream; the host never
+// waits for the device inside an iteration.  Convergence is decided on the device (pmx_ctl): once
+// `done` is set every later kernel returns immediately, so (A, S, G) stay frozen at exactly the
+// iteration where the reference would `break`, while the host polls the flag only every
+// `check_every` iterations.
+#include <math.h>
+
+#include "kernels.h"
+#include "grad_umma.h"
+
+int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
+
+struct pmx_nmf {
+  pmx_ctx* ctx;
+  int M, N, K;   // N = local number of columns (this rank's stripe of Y and S)
+  int ldY;       // leading dimension of the device copy of Y (N rounded up to 4: TMA needs 16-byte row pitch)
+  float *Y, *A, *S, *A_old, *S_old, *Ae, *Se, *GA, *GS;
+  double *gramA, *gramS;
+  pmx_ctl* ctl;     // device
+  pmx_ctl* h_ctl;   // pinned host mirror
+  UmmaPlan* plan;   // tcgen05 gradient kernel state (tensor maps, bf16 operand buffers); lazily built
+  // ---- pgm
+  pmx_pgm_opts pgm;
+  ProxChain chA, chS;
+  double nest_t;
+  int it_enqueued;
+  // ---- adaprox
+  pmx_adaprox_opts ada;
+  float *MA, *MS, *VA, *VS, *VhA, *VhS, *Psi, *Z0, *Z1, *alphaA, *alphaS;
+  int ada_it;
+  // ---- bsdmm
+  pmx_bsdmm_opts bs;
+  float* Zg[2][4];
+  float* Ug[2][4];
+  double* bs_norms;  // device: [2 blocks][4 constraints][5 norms]
+  int bs_it;
+};
+
+namespace {
+
+__global__ void k_pgm_finalize(pmx_ctl* ctl, float e2A, float e2S) {
+  if (ctl->done) return;
+  // algorithms.py:130-133: l2sq(X - X_) <= e_rel**2 * l2sq(X), evaluated in fp32 like the reference
+  const bool cA = (float)ctl->norms[0] <= e2A * (float)ctl->norms[1];
+  const bool cS = (float)ctl->norms[3] <= e2S * (float)ctl->norms[4];
+  ctl->conv[0] = cA;
+  ctl->conv[1] = cS;
+  ctl->it += 1;
+  if (cA && cS) ctl->done = 1;
+}
+
+__global__ void k_ctl_clear_norms(pmx_ctl* ctl) {
+  if (ctl->done) return;
+  for (int i = threadIdx.x; i < 8; i += blockDim.x) ctl->norms[i] = 0.0;
+}
+
+int alloc_f(float** p, size_t n) {
+  PMX_CUDA(cudaMalloc((void**)p, sizeof(float) * (n ? n : 1)));
+  return PMX_OK;
+}
+
+int pull_ctl(pmx_nmf* h) {
+  PMX_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(pmx_ctl), cudaMemcpyDeviceToHost, h->ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return PMX_OK;
+}
+
+}  // namespace
+
+// gradient at (A, S) into (GA, GS) [+ loss], kernel selection, multi-GPU sum of the G_A partials
+int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* GS, double* loss, int kernel,
+                 const int* done) {
+  pmx_ctx* ctx = h->ctx;
+  bool use_umma = false;
+  if (kernel == 2) use_umma = true;
+  if (kernel == 0) use_umma = umma_supported(h->M, h->N, h->K) && (long long)h->M * h->N >= 128LL * 128;
+  if (use_umma) {
+    if (!umma_supported(h->M, h->N, h->K)) {
+      pmx_set_error("tcgen05 gradient kernel does not support M=%d N=%d K=%d", h->M, h->N, h->K);
+      return PMX_ERR_UNSUPPORTED;
+    }
+    if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
+    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done));
+  } else {
+    PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, A, S, h->M, h->N, h->K, GA, GS, loss, done));
+  }
+  if (ctx->world > 1) {
+    PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
+    if (loss) PMX_CHECK(pmx_comm_allreduce_internal(ctx, loss, 1, 1, ctx->stream));
+  }
+  return PMX_OK;
+}
+
+// lip/step of both blocks at (A, S): step[0] = 1/lambda_max(S S^T), step[1] = 1/lambda_max(A^T A)
+// (nmf.py:44-49).  Runs on the aux stream so that it overlaps the gradient kernel.
+int nmf_steps(pmx_nmf* h, const float* A, const float* S, bool need_A, bool need_S) {
+  pmx_ctx* ctx = h->ctx;
+  PMX_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+  if (need_A) {  // step for A needs the Gram of S (sum over this rank's columns, then over ranks)
+    PMX_CHECK(launch_gram(ctx, ctx->aux, S, h->K, h->N, false, h->gramS, &h->ctl->done));
+    if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->aux));
+    PMX_CHECK(launch_lambda_max(ctx, ctx->aux, h->gramS, h->K, h->ctl, 0));
+  }
+  if (need_S) {
+    PMX_CHECK(launch_gram(ctx, ctx->aux, A, h->M, h->K, true, h->gramA, &h->ctl->done));
+    PMX_CHECK(launch_lambda_max(ctx, ctx->aux, h->gramA, h->K, h->ctl, 1));
+  }
+  PMX_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
+  return PMX_OK;
+}
+int nmf_steps_join(pmx_nmf* h) {
+  PMX_CUDA(cudaStreamWaitEvent(h->ctx->stream, h->ctx->ev_join, 0));
+  return PMX_OK;
+}
+
+extern "C" {
+
+int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
+  PMX_REQUIRE(ctx && out, "NULL argument");
+  PMX_REQUIRE(M > 0 && N_local > 0 && K > 0, "shape must be positive");
+  PMX_REQUIRE(K <= 128, "K <= 128 is supported");
+  pmx_nmf* h = new pmx_nmf();
+  memset(h, 0, sizeof(*h));
+  h->ctx = ctx;
+  h->M = M;
+  h->N = N_local;
+  h->K = K;
+  h->ldY = (N_local + 3) & ~3;
+  PMX_CUDA(cudaSetDevice(ctx->device));
+  const size_t mk = (size_t)M * K, kn = (size_t)K * N_local;
+  PMX_CHECK(alloc_f(&h->Y, (size_t)M * h->ldY));
+  PMX_CHECK(alloc_f(&h->A, mk));
+  PMX_CHECK(alloc_f(&h->S, kn));
+  PMX_CHECK(alloc_f(&h->A_old, mk));
+  PMX_CHECK(alloc_f(&h->S_old, kn));
+  PMX_CHECK(alloc_f(&h->GA, mk));
+  PMX_CHECK(alloc_f(&h->GS, kn));
+  PMX_CUDA(cudaMalloc((void**)&h->gramA, sizeof(double) * K * K));
+  PMX_CUDA(cudaMalloc((void**)&h->gramS, sizeof(double) * K * K));
+  PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(pmx_ctl)));
+  PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)M * h->ldY, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->GA, 0, sizeof(float) * mk, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->GS, 0, sizeof(float) * kn, ctx->stream));
+  PMX_CUDA(cudaMallocHost((void**)&h->h_ctl, sizeof(pmx_ctl)));
+  *out = h;
+  return PMX_OK;
+}
+
+int pmx_nmf_destroy(pmx_nmf* h) {
+  if (!h) return PMX_OK;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaStreamSynchronize(h->ctx->aux);
+  float* bufs[] = {h->Y, h->A, h->S, h->A_old, h->S_old, h->Ae, h->Se, h->GA, h->GS, h->MA, h->MS, h->VA, h->VS,
+                   h->VhA, h->VhS, h->Psi, h->Z0, h->Z1, h->alphaA, h->alphaS};
+  for (float* b : bufs)
+    if (b) cudaFree(b);
+  for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < 4; ++i) {
+      if (h->Zg[j][i]) cudaFree(h->Zg[j][i]);
+      if (h->Ug[j][i]) cudaFree(h->Ug[j][i]);
+    }
+  if (h->bs_norms) cudaFree(h->bs_norms);
+  cudaFree(h->gramA);
+  cudaFree(h->gramS);
+  cudaFree(h->ctl);
+  cudaFreeHost(h->h_ctl);
+  if (h->plan) umma_plan_destroy(h->plan);
+  delete h;
+  return PMX_OK;
+}
+
+int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncols) {
+  PMX_REQUIRE(h && host_Y, "NULL argument");
+  PMX_REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= h->N, "column range outside the local stripe");
+  PMX_CUDA(cudaMemcpy2DAsync(h->Y + col0, sizeof(float) * h->ldY, host_Y, sizeof(float) * ld, sizeof(float) * ncols,
+                             h->M, cudaMemcpyHostToDevice, h->ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return PMX_OK;
+}
+
+static int which_ptr(pmx_nmf* h, int which, float** p, size_t* n) {
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  switch (which) {
+    case PMX_A: *p = h->A; *n = mk; break;
+    case PMX_S: *p = h->S; *n = kn; break;
+    case PMX_GA: *p = h->GA; *n = mk; break;
+    case PMX_GS: *p = h->GS; *n = kn; break;
+    case PMX_MA: *p = h->MA; *n = mk; break;
+    case PMX_MS: *p = h->MS; *n = kn; break;
+    case PMX_VA: *p = h->VA; *n = mk; break;
+    case PMX_VS: *p = h->VS; *n = kn; break;
+    case PMX_VHA: *p = h->VhA; *n = mk; break;
+    case PMX_VHS: *p = h->VhS; *n = kn; break;
+    default: pmx_set_error("unknown buffer id %d", which); return PMX_ERR_ARG;
+  }
+  if (!*p) {
+    pmx_set_error("buffer %d is not allocated in this solver state", which);
+    return PMX_ERR_ARG;
+  }
+  return PMX_OK;
+}
+
+int pmx_nmf_set(pmx_nmf* h, int which, const float* host_src) {
+  PMX_REQUIRE(h && host_src, "NULL argument");
+  float* p; size_t n;
+  PMX_CHECK(which_ptr(h, which, &p, &n));
+  return pmx_h2d(h->ctx, p, host_src, n * sizeof(float));
+}
+
+int pmx_nmf_get(pmx_nmf* h, int which, float* host_dst) {
+  PMX_REQUIRE(h && host_dst, "NULL argument");
+  float* p; size_t n;
+  PMX_CHECK(which_ptr(h, which, &p, &n));
+  return pmx_d2h(h->ctx, host_dst, p, n * sizeof(float));
+}
+
+int pmx_nmf_device_ptr(pmx_nmf* h, int which, float** dev_ptr) {
+  PMX_REQUIRE(h && dev_ptr, "NULL argument");
+  size_t n;
+  return which_ptr(h, which, dev_ptr, &n);
+}
+
+int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
+  PMX_REQUIRE(h && loss_host, "NULL argument");
+  // scratch gradients: the loss is a by-product of the residual pass
+  float *ga, *gs;
+  PMX_CHECK(alloc_f(&ga, (size_t)h->M * h->K));
+  PMX_CHECK(alloc_f(&gs, (size_t)h->K * h->N));
+  int st = nmf_gradient(h, h->A, h->S, ga, gs, &h->ctl->norms[6], 0, nullptr);
+  if (st == PMX_OK) st = pull_ctl(h);
+  cudaFree(ga);
+  cudaFree(gs);
+  *loss_host = h->h_ctl->norms[6];
+  return st;
+}
+
+// ------------------------------------------------------------------ PGM
+int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
+  PMX_REQUIRE(h && opts, "NULL argument");
+  h->pgm = *opts;
+  if (h->pgm.check_every <= 0) h->pgm.check_every = 8;
+  h->chA = make_chain(&opts->prox_A);
+  h->chS = make_chain(&opts->prox_S);
+  h->nest_t = 1.0;  // utils.py:195
+  h->it_enqueued = 0;
+  if (opts->accelerated) {
+    if (!h->Ae) PMX_CHECK(alloc_f(&h->Ae, (size_t)h->M * h->K));
+    if (!h->Se) PMX_CHECK(alloc_f(&h->Se, (size_t)h->K * h->N));
+  }
+  PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  return PMX_OK;
+}
+
+static int pgm_enqueue_iteration(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  const int* done = &h->ctl->done;
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  // Nesterov sequence (utils.py:198-206), in double like the reference's Python floats
+  double omega = 0.0;
+  if (h->pgm.accelerated) {
+    const double t_next = 0.5 * (1.0 + sqrt(4.0 * h->nest_t * h->nest_t + 1.0));
+    omega = (h->nest_t - 1.0) / t_next;
+    h->nest_t = t_next;
+  }
+  const float* Ae = h->A;
+  const float* Se = h->S;
+  if (omega > 0.0) {  // algorithms.py:94-95
+    PMX_CHECK(launch_extrapolate(ctx, h->A, h->A_old, h->Ae, mk, (float)omega, done));
+    PMX_CHECK(launch_extrapolate(ctx, h->S, h->S_old, h->Se, kn, (float)omega, done));
+    Ae = h->Ae;
+    Se = h->Se;
+  }
+  k_ctl_clear_norms<<<1, 32, 0, ctx->stream>>>(h->ctl);
+  PMX_LAUNCHED(ctx);
+  // steps on the side stream, gradient on the main stream (both read the same point, algorithms.py:105-106)
+  PMX_CHECK(nmf_steps(h, Ae, Se, true, true));
+  PMX_CHECK(nmf_gradient(h, Ae, Se, h->GA, h->GS, nullptr, h->pgm.kernel, done));
+  PMX_CHECK(nmf_steps_join(h));
+  // X[j][:] = prox[j](_X[j] - S[j]*G[j], S[j])   (algorithms.py:107-108) + norms (:130-133) + X_ copy (:102)
+  UpdIO io;
+  memset(&io, 0, sizeof(io));
+  io.done = done;
+  io.step.mode = 1;
+  io.step.scale = 1.f;
+  io.Xin = Ae; io.G = h->GA; io.Xprev = h->A; io.Xout = h->A; io.Xold_out = h->A_old;
+  io.norms = &h->ctl->norms[0]; io.rows = h->M; io.cols = h->K; io.step.ptr = &h->ctl->step[0];
+  PMX_CHECK(launch_update(ctx, IN_PGM, h->chA, io));
+  io.Xin = Se; io.G = h->GS; io.Xprev = h->S; io.Xout = h->S; io.Xold_out = h->S_old;
+  io.norms = &h->ctl->norms[3]; io.rows = h->K; io.cols = h->N; io.step.ptr = &h->ctl->step[1];
+  PMX_CHECK(launch_update(ctx, IN_PGM, h->chS, io));
+  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+  const float eA = h->pgm.e_rel_A, eS = h->pgm.e_rel_S;
+  k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, (float)((double)eA * (double)eA), (float)((double)eS * (double)eS));
+  PMX_LAUNCHED(ctx);
+  h->it_enqueued += 1;
+  return pmx_check_launch(ctx, "pgm iteration");
+}
+
+int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* conv_S, float* step_A, float* step_S) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  PMX_REQUIRE(n_iter >= 0, "n_iter must be >= 0");
+  PMX_CHECK(pull_ctl(h));
+  const int it0 = h->h_ctl->it;
+  bool stopped = h->h_ctl->done != 0;
+  for (int i = 0; i < n_iter && !stopped; ++i) {
+    PMX_CHECK(pgm_enqueue_iteration(h));
+    if ((i + 1) % h->pgm.check_every == 0 && i + 1 < n_iter) {
+      PMX_CHECK(pull_ctl(h));
+      stopped = h->h_ctl->done != 0;
+    }
+  }
+  PMX_CHECK(pull_ctl(h));
+  if (iters_done) *iters_done = h->h_ctl->it - it0;
+  if (conv_A) *conv_A = h->h_ctl->conv[0];
+  if (conv_S) *conv_S = h->h_ctl->conv[1];
+  if (step_A) *step_A = h->h_ctl->step[0];
+  if (step_S) *step_S = h->h_ctl->step[1];
+  if (h->h_ctl->nonfinite) {
+    pmx_set_error("Gram matrix contains infs or NaNs (iteration %d)", h->h_ctl->it);
+    return PMX_ERR_NONFINITE;
+  }
+  return PMX_OK;
+}
+
+int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, int M, int N, int K, float* G_A,
+                 float* G_S, double* loss_or_null, int kernel) {
+  PMX_REQUIRE(ctx && Y && A && S && G_A && G_S, "NULL argument");
+  PMX_REQUIRE(M > 0 && N > 0 && K > 0, "shape must be positive");
+  bool use_umma = (kernel == 2) || (kernel == 0 && umma_supported(M, N, K) && (N % 4 == 0) &&
+                                    (long long)M * N >= 128LL * 128);
+  if (use_umma) {
+    if (!umma_supported(M, N, K) || (N % 4) != 0) {
+      pmx_set_error("tcgen05 gradient kernel needs K <= 64 and N %% 4 == 0 (M=%d N=%d K=%d)", M, N, K);
+      return PMX_ERR_UNSUPPORTED;
+    }
+    UmmaPlan* plan = nullptr;
+    PMX_CHECK(umma_plan_create(ctx, Y, N, M, N, K, &plan));
+    int st = launch_grad_umma(ctx, plan, A, S, G_A, G_S, loss_or_null, nullptr);
+    cudaStreamSynchronize(ctx->stream);
+    umma_plan_destroy(plan);
+    return st;
+  }
+  return launch_grad_simt(ctx, Y, N, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);
+}
+
+int pmx_nmf_lipschitz(pmx_ctx* ctx, const float* A, const float* S, int M, int N, int K, float* lip_A_host,
+                      float* lip_S_host) {
+  PMX_REQUIRE(ctx && A && S, "NULL argument");
+  double* gram;
+  pmx_ctl* ctl;
+  PMX_CUDA(cudaMalloc((void**)&gram, sizeof(double) * K * K * 2));
+  PMX_CUDA(cudaMalloc((void**)&ctl, sizeof(pmx_ctl)));
+  PMX_CUDA(cudaMemsetAsync(ctl, 0, sizeof(pmx_ctl), ctx->stream));
+  int st = launch_gram(ctx, ctx->stream, S, K, N, false, gram, nullptr);
+  if (st == PMX_OK) st = launch_lambda_max(ctx, ctx->stream, gram, K, ctl, 0);
+  if (st == PMX_OK) st = launch_gram(ctx, ctx->stream, A, M, K, true, gram + (size_t)K * K, nullptr);
+  if (st == PMX_OK) st = launch_lambda_max(ctx, ctx->stream, gram + (size_t)K * K, K, ctl, 1);
+  pmx_ctl hc;
+  memset(&hc, 0, sizeof(hc));
+  if (st == PMX_OK) {
+    cudaError_t e = cudaMemcpyAsync(&hc, ctl, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      pmx_set_error("pmx_nmf_lipschitz: %s", cudaGetErrorString(e));
+      st = PMX_ERR_CUDA;
+    }
+  }
+  cudaFree(gram);
+  cudaFree(ctl);
+  if (st != PMX_OK) return st;
+  if (lip_A_host) *lip_A_host = hc.lip[0];  // Lipschitz constant of grad_A = lambda_max(S S^T)
+  if (lip_S_host) *lip_S_host = hc.lip[1];
+  if (hc.nonfinite) {
+    pmx_set_error("Array must not contain infs or NaNs");
+    return PMX_ERR_NONFINITE;
+  }
+  return PMX_OK;
+}
+
+}  // extern "C"

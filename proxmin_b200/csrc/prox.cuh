@@ -1,0 +1,111 @@
+// Proximal-operator chains and the fused "forward step + prox + norms" kernel family.
+//
+// Replaces proxmin/operators.py:20-160 (elementwise maps), AlternatingProjections
+// (:187-211), the update line of pgm (algorithms.py:107-108), the convergence norms
+// (algorithms.py:130-133, utils.py:257-260) and the proximal sub-iteration of adaprox
+// (algorithms.py:386-393).  All of these are HBM-bound elementwise passes, so one
+// kernel family does "load -> transform -> prox chain -> store -> norms" in a single
+// pass whenever the chain allows it.
+#pragma once
+#include "common.cuh"
+
+struct ProxChain {  // device-side copy of pmx_prox (passed by value as a kernel argument)
+  int n;
+  int op[PMX_MAX_OPS];
+  int rel[PMX_MAX_OPS];
+  int axis[PMX_MAX_OPS];
+  float thr[PMX_MAX_OPS];
+};
+
+static inline ProxChain make_chain(const pmx_prox* p) {
+  ProxChain c;
+  memset(&c, 0, sizeof(c));
+  if (!p) return c;
+  c.n = p->n_ops;
+  for (int i = 0; i < p->n_ops && i < PMX_MAX_OPS; ++i) {
+    c.op[i] = p->ops[i].op;
+    c.rel[i] = p->ops[i].relative;
+    c.axis[i] = p->ops[i].axis;
+    c.thr[i] = p->ops[i].thresh;
+  }
+  return c;
+}
+
+// position of the first UNITY op at or after `from` (or c.n)
+__host__ __device__ inline int chain_next_unity(const ProxChain& c, int from) {
+  int i = from;
+  while (i < c.n && c.op[i] != PMX_OP_UNITY) ++i;
+  return i;
+}
+static inline int chain_unity_axis(const ProxChain& c) {  // -1 none, 0/1 the single axis used, 2 mixed
+  int ax = -1;
+  for (int i = 0; i < c.n; ++i)
+    if (c.op[i] == PMX_OP_UNITY) {
+      if (ax == -1) ax = c.axis[i];
+      else if (ax != c.axis[i]) ax = 2;
+    }
+  return ax;
+}
+
+// One elementwise primitive.  The comparisons are written exactly like the NumPy masks of
+// the reference so that NaN, +-inf and -0.0 behave identically (support sets are bit-exact).
+__device__ __forceinline__ float prox_elem(float x, int op, float t) {
+  switch (op) {
+    case PMX_OP_ZERO: return 0.0f;                                   // operators.py:29
+    case PMX_OP_PLUS: return (x < 0.0f) ? 0.0f : x;                   // operators.py:36-37
+    case PMX_OP_MIN:  return (x - t < 0.0f) ? t : x;                  // operators.py:67-68
+    case PMX_OP_MAX:  return (x - t > 0.0f) ? t : x;                  // operators.py:82-83
+    case PMX_OP_HARD: return (fabsf(x) < t) ? 0.0f : x;               // operators.py:124-125
+    case PMX_OP_SOFT: {                                               // operators.py:150
+      float a = fabsf(x) - t;
+      a = (a < 0.0f) ? 0.0f : a;                                      // prox_plus of |X|-t
+      float s = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : ((x == 0.0f) ? 0.0f : x));  // np.sign
+      return s * a;
+    }
+    default: return x;
+  }
+}
+
+// apply the elementwise ops [a, b) of the chain
+__device__ __forceinline__ float chain_segment(const ProxChain& c, int a, int b, float x, float step) {
+  for (int i = a; i < b; ++i) {
+    float t = c.rel[i] ? c.thr[i] * step : c.thr[i];  // operators.py:4-14 in fp32 (NumPy weak-scalar rule)
+    x = prox_elem(x, c.op[i], t);
+  }
+  return x;
+}
+
+// How the per-element step / threshold scale is obtained.
+struct StepSpec {
+  const float* ptr;  // device pointer (modes 1..3)
+  int mode;          // 0 host scalar `value`; 1 *ptr; 2 ptr[col]; 3 ptr[row]
+  float scale;       // multiplies the device value (backtracking T_j, slack)
+  float value;
+};
+__device__ __forceinline__ float step_at(const StepSpec& s, int row, int col) {
+  switch (s.mode) {
+    case 1: return s.ptr[0] * s.scale;
+    case 2: return s.ptr[col] * s.scale;
+    case 3: return s.ptr[row] * s.scale;
+    default: return s.value;
+  }
+}
+
+enum { IN_PLAIN = 0, IN_PGM = 1, IN_ADASUB = 2 };
+
+struct UpdIO {
+  const float* Xin;    // point the transform starts from (X, extrapolated X, or z)
+  const float* G;      // IN_PGM: gradient;  IN_ADASUB: Psi
+  const float* X0;     // IN_ADASUB: X after the moment step (algorithms.py:378)
+  const float* Xprev;  // norms compare the result against this (may alias Xout)
+  float* Xout;
+  float* Xold_out;     // optional: receives a copy of Xprev (algorithms.py:102)
+  double* norms;       // optional: += { |out-prev|^2, |out|^2, |prev|^2 }
+  const int* done;     // optional early-exit flag(s): skip when *done != 0
+  const int* done2;
+  const float* psimax; // IN_ADASUB: max(Psi) (algorithms.py:384)
+  int rows, cols;
+  StepSpec step;       // IN_PGM: step; IN_ADASUB: Alpha; IN_PLAIN: step handed to the prox
+};
+
+int launch_update(pmx_ctx* ctx, int in_kind, const ProxChain& chain, const UpdIO& io);
