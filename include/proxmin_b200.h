@@ -50,6 +50,11 @@ int pmx_ctx_launch_count(pmx_ctx* ctx, long long* count);
 /* name/SM count/memory of the device behind the context */
 int pmx_ctx_device_info(pmx_ctx* ctx, char* name, int name_len, int* sm_count, size_t* total_mem);
 
+/* per-launch CUDA-event timing of the dominant kernel (the fused gradient kernel), recorded on the
+ * stream it is launched on; read returns the summed duration and the number of launches timed */
+int pmx_ctx_profile(pmx_ctx* ctx, int enable);
+int pmx_ctx_profile_read(pmx_ctx* ctx, float* total_ms, int* launches);
+
 /* multi-GPU: one process per GPU; `unique_id` (128 bytes) is produced by
  * pmx_comm_unique_id on rank 0 and distributed by the host (bench.py uses
  * torch.distributed/gloo for that plumbing).  Collectives are NCCL all-reduces
@@ -200,15 +205,40 @@ int pmx_admm_init_zu(pmx_admm* h);
 /* one pass of utils.py:307-346 + :366-391 with step_f (already multiplied by slack) and
  * step_g_i = step_f * n_g (utils.py:279); fills errors[4*i..] = e_pri, e_dual, |R|, |S| per constraint,
  * *converged, and *stalled = (X and every R_i bit-identical to the previous pass, algorithms.py:506,635) */
-int pmx_admm_step(pmx_admm* h, float step_f, int* converged, int* stalled, double* errors);
+int pmx_admm_step(pmx_admm* h, double step_f, int* converged, int* stalled, double* errors);
 /* fused loop of admm/sdmm iterations with constant step_f: device-side stop flag, no host round trips */
-int pmx_admm_run(pmx_admm* h, float step_f, int max_iter, int* iters_logged, int* converged, double* errors);
+int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, int* converged, double* errors);
 
 /* ------------------------------------------------ elementwise solver primitives (generic callback path)
  * Used by the Python solvers when grad/step/prox are arbitrary user callables
  * (algorithms.py:107-108, 130-133): X_new = prox(Xe - step*G); returns the two norms. */
 int pmx_pgm_update(pmx_ctx* ctx, const pmx_prox* prox, const float* dev_Xe, const float* dev_G, float* dev_X,
                    int rows, int cols, float step, double* norm_diff_sq, double* norm_new_sq);
+
+/* single elementwise expression on device arrays (callback loops; all operands length n).
+ * red_host (optional, 5 doubles) receives the reductions of the opcode. */
+typedef enum {
+  PMX_EW_EXTRAP = 0,  /* o0 = a + s0*(a - b)                     algorithms.py:95                 */
+  PMX_EW_ADD = 1,     /* o0 = a + b                               utils.py:297                     */
+  PMX_EW_SUB = 2,     /* o0 = a - b                               utils.py:317,338                 */
+  PMX_EW_DX_ACC = 3,  /* o0 = d + s0*(a - b + c)   (d may be NULL) utils.py:316,333                */
+  PMX_EW_ZU = 4,      /* a=X b=Z' c=Z d=U s0=-1/step_g s1=step_g|0: o0=R o1=S o2=U+R;
+                         red = |X|^2 |Z'|^2 |U'(/s1)|^2 |R|^2 |S|^2   utils.py:299-303,349-363 */
+  PMX_EW_DOT_DIFF = 5,/* red = sum((a-b)*c), sum((a-b)^2)         algorithms.py:118                */
+  PMX_EW_MAXABS = 6,  /* red[0] = max|s0*a|                       algorithms.py:121                */
+  PMX_EW_SUMSQ = 7    /* red[0] = sum(a^2)                        utils.py:257-260                 */
+} pmx_ew_op;
+int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const float* c, const float* d, float s0,
+           float s1, float* o0, float* o1, float* o2, double* red_host);
+
+/* adaprox building blocks on caller-owned device arrays (callback loop of algorithms.py:365-410).
+ * alpha: mode 0 = scalar alpha_value, 2 = per-column vector alpha_dev[cols], 3 = per-row vector alpha_dev[rows]. */
+int pmx_adaprox_moments(pmx_ctx* ctx, int scheme, const float* G, float* M, float* V, float* Vhat_or_null, float* X,
+                        float* Psi, int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value,
+                        double b1, double b1_prev, float b2, float eps, float p, int t, float* psimax_host);
+int pmx_adaprox_sub(pmx_ctx* ctx, const pmx_prox* prox, const float* Z, const float* X, const float* Psi, float* Zout,
+                    int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value, float psimax,
+                    double* norms_host);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ OP_ID, OP_ZERO, OP_PLUS, OP_UNITY, OP_MIN, OP_MAX, OP_HARD, OP_SOFT = range(8)
 A, S, GA, GS, MA, MS, VA, VS, VHA, VHS = range(10)
 SCHEMES = {"adam": 0, "nadam": 1, "amsgrad": 2, "padam": 3, "adamx": 4, "radam": 5}
 
+EW_EXTRAP, EW_ADD, EW_SUB, EW_DX_ACC, EW_ZU, EW_DOT_DIFF, EW_MAXABS, EW_SUMSQ = range(8)
 ERR_CUDA, ERR_ARG, ERR_NCCL, ERR_UNSUPPORTED, ERR_NONFINITE = -1, -2, -3, -4, -5
 
 
@@ -83,6 +84,8 @@ def _declare(L):
         "pmx_ctx_sync": [vp],
         "pmx_ctx_launch_count": [vp, C.POINTER(C.c_longlong)],
         "pmx_ctx_device_info": [vp, C.c_char_p, i32, pi, C.POINTER(sz)],
+        "pmx_ctx_profile": [vp, i32],
+        "pmx_ctx_profile_read": [vp, pf, pi],
         "pmx_comm_unique_id": [vp],
         "pmx_comm_init": [vp, vp, i32, i32],
         "pmx_comm_allreduce_sum": [vp, vp, sz],
@@ -117,9 +120,13 @@ def _declare(L):
         "pmx_admm_set": [vp, vp, vp],
         "pmx_admm_get": [vp, vp],
         "pmx_admm_init_zu": [vp],
-        "pmx_admm_step": [vp, f32, pi, pi, pd],
-        "pmx_admm_run": [vp, f32, i32, pi, pi, pd],
+        "pmx_admm_step": [vp, C.c_double, pi, pi, pd],
+        "pmx_admm_run": [vp, C.c_double, i32, pi, pi, pd],
         "pmx_pgm_update": [vp, C.POINTER(Prox), vp, vp, vp, i32, i32, f32, pd, pd],
+        "pmx_ew": [vp, i32, sz, vp, vp, vp, vp, f32, f32, vp, vp, vp, pd],
+        "pmx_adaprox_moments": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, f32, C.c_double, C.c_double,
+                                f32, f32, f32, i32, pf],
+        "pmx_adaprox_sub": [vp, C.POINTER(Prox), vp, vp, vp, vp, i32, i32, vp, i32, f32, f32, pd],
     }
     for name, args in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree: fail loudly
@@ -175,6 +182,14 @@ class Context:
         sm, mem = C.c_int(0), C.c_size_t(0)
         check(lib().pmx_ctx_device_info(self.handle, name, 128, C.byref(sm), C.byref(mem)))
         return name.value.decode(), sm.value, mem.value
+
+    def profile(self, enable):
+        check(lib().pmx_ctx_profile(self.handle, int(enable)))
+
+    def profile_read(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        check(lib().pmx_ctx_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # -- memory
     def malloc(self, nbytes):

@@ -20,6 +20,7 @@ from functools import partial
 
 import numpy as np
 
+from . import _dev
 from . import _ffi
 from . import operators
 from . import utils
@@ -207,7 +208,7 @@ def _pgm_callbacks(X, grad, step, prox, accelerated, backtracking, f, e_rel, max
             callback(*X, it=it)
             omega = accel.omega
             if omega > 0:
-                _X = tuple(X[j] + omega * (X[j] - X_[j]) for j in range(N))  # noqa: F821 (host glue on user arrays)
+                _X = tuple(_dev.extrapolate(X[j], X_[j], omega) for j in range(N))  # noqa: F821
             elif backtracking:
                 _X = utils._copy_tuple(X)
             else:
@@ -223,10 +224,8 @@ def _pgm_callbacks(X, grad, step, prox, accelerated, backtracking, f, e_rel, max
                 f_now = f(*X)
                 if it == 0:
                     f_prev = f(*X_)
-                while f_now > f_prev + np.sum(
-                    [np.sum((X[j] - X_[j]) * G[j]) + 0.5 / (T[j] * S[j]) * np.sum((X[j] - X_[j]) ** 2)
-                     for j in range(N)]):
-                    jmax = np.argmax([np.max(np.abs(S[j] * G[j])) / np.max(np.abs(X_[j])) for j in range(N)])
+                while f_now > f_prev + _quadratic_model(X, X_, G, T, S):
+                    jmax = int(np.argmax([_dev.maxabs(G[j], _scalar_step(S[j])) / _dev.maxabs(X_[j]) for j in range(N)]))
                     T[jmax] /= 2
                     norms[jmax] = _update_block(chains[jmax], prox[jmax], _X[jmax], G[jmax], X[jmax], X_[jmax],
                                                 T[jmax] * S[jmax])
@@ -265,27 +264,566 @@ def _dev_diff_norms(X, Xold):
     return nd, nn
 
 
+
+def _quadratic_model(X, X_, G, T, S):
+    """sum_j <X_j - X_j_old, G_j> + |X_j - X_j_old|^2 / (2 T_j S_j)   (Beck & Teboulle eq. 3.2, algorithms.py:118)"""
+    tot = 0.0
+    for j in range(len(X)):
+        dot, sq = _dev.dot_diff(X[j], X_[j], G[j])
+        tot += dot + 0.5 / (T[j] * _scalar_step(S[j])) * sq
+    return tot
+
+
 # ------------------------------------------------------------------------------------------
-# placeholders filled in below
+# adaprox
 # ------------------------------------------------------------------------------------------
-def adaprox(X, grad, step, prox=None, scheme="adam", b1=0.9, b2=0.999, eps=1e-8, check_convergence=True,
-            p=0.25, e_rel=1e-6, max_iter=1000, prox_max_iter=1000, M=None, V=None, Vhat=None, callback=None):
-    raise NotImplementedError
+def adaprox(
+    X,
+    grad,
+    step,
+    prox=None,
+    scheme="adam",
+    b1=0.9,
+    b2=0.999,
+    eps=1e-8,
+    check_convergence=True,
+    p=0.25,
+    e_rel=1e-6,
+    max_iter=1000,
+    prox_max_iter=1000,
+    M=None,
+    V=None,
+    Vhat=None,
+    callback=None,
+):
+    """Adaptive proximal gradient method: Adam, NAdam, AMSGrad, PAdam, AdamX, RAdam with proximal
+    sub-iterations (algorithms.py:248-423).  Returns ``(converged, M, V, Vhat)``; X is updated in place."""
+    X = utils._as_tuple(X)
+    N = len(X)
+    prox = utils._as_tuple(prox)
+    if len(prox) == 1:
+        prox = prox * N
+    assert len(prox) == len(X)
+
+    if np.isscalar(e_rel):
+        e_rel = (e_rel,) * N
+    assert len(e_rel) == len(X)
+
+    if not hasattr(b1, "__iter__"):
+        b1 = np.array((b1,) * max_iter)
+    assert len(b1) == max_iter
+    assert (b1 >= 0).all() and (b1 < 1).all()
+
+    assert b2 >= 0 and b2 < 1
+    assert eps >= 0
+    assert p > 0 and p <= 0.5
+    scheme = scheme.lower()
+    assert scheme in ["adam", "nadam", "adamx", "amsgrad", "padam", "radam"]
+
+    if M is not None:
+        assert len(M) == N and all(m.shape == x.shape for x, m in zip(X, M))
+    if V is not None:
+        assert len(V) == N and all(v.shape == x.shape for x, v in zip(X, V))
+    if Vhat is not None:
+        assert len(Vhat) == N and all(vhat.shape == x.shape for x, vhat in zip(X, Vhat))
+
+    Y = _nmf_grad_target(grad)
+    chains = _describe_all(prox, allow_none=True)
+    if (Y is not None and chains is not None and _is_factor_pair(X) and _is_step(step, "step_adaprox")):
+        return _adaprox_nmf_device(X, Y, chains, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter,
+                                   prox_max_iter, M, V, Vhat, callback)
+    return _adaprox_callbacks(X, grad, step, prox, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter,
+                              prox_max_iter, M, V, Vhat, callback)
 
 
-def admm(X, prox_f, step_f, prox_g=None, step_g=None, L=None, e_rel=1e-6, e_abs=0, max_iter=1000, callback=None):
-    raise NotImplementedError
+def _b1_prev(b1):
+    b1 = np.asarray(b1, dtype=np.float64)
+    return np.concatenate((b1[-1:], b1[:-1]))  # b1[it - 1] with Python's wrap-around at it = 0 (algorithms.py:213)
 
 
-def sdmm(X, prox_f, step_f, proxs_g=None, steps_g=None, Ls=None, e_rel=1e-6, e_abs=0, max_iter=1000,
-         callback=None):
-    raise NotImplementedError
+def _adaprox_nmf_device(X, Y, chains, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter, prox_max_iter,
+                        M, V, Vhat, callback):
+    from . import nmf as _nmf
+
+    A, S = X
+    dt = np.result_type(A.dtype, S.dtype)
+    prob = _nmf.Problem(Y, A, S)
+    b1 = np.asarray(b1, dtype=np.float64)
+    b1p = _b1_prev(b1)
+    try:
+        prob.adaprox_begin(chains[0], chains[1], scheme, b2, eps, p, e_rel, check_convergence, prox_max_iter,
+                           has_vhat=Vhat is not None)
+        if M is not None:
+            prob.set(_ffi.MA, M[0]); prob.set(_ffi.MS, M[1])
+        if V is not None:
+            prob.set(_ffi.VA, V[0]); prob.set(_ffi.VS, V[1])
+        if Vhat is not None:
+            prob.set(_ffi.VHA, Vhat[0]); prob.set(_ffi.VHS, Vhat[1])
+        done, converged, sub = 0, (False, False), (0, 0)
+        if callback is None:
+            done, converged, sub = prob.adaprox_run(max_iter, b1, b1p)
+        else:
+            for it in range(max_iter):
+                try:
+                    callback(*X, it=it)
+                except StopIteration:
+                    break
+                prob.set(_ffi.A, A)
+                prob.set(_ffi.S, S)
+                n, converged, sub = prob.adaprox_run(1, b1[it:it + 1], b1p[it:it + 1])
+                done += n
+                _writeback(prob, X)
+                if check_convergence and all(converged):
+                    break
+        _writeback(prob, X)
+        if M is None:
+            M = (prob.get(_ffi.MA, dtype=dt), prob.get(_ffi.MS, dtype=dt))
+        else:
+            prob.get(_ffi.MA, out=M[0]); prob.get(_ffi.MS, out=M[1])
+        if V is None:
+            V = (prob.get(_ffi.VA, dtype=dt), prob.get(_ffi.VS, dtype=dt))
+        else:
+            prob.get(_ffi.VA, out=V[0]); prob.get(_ffi.VS, out=V[1])
+        if Vhat is None:
+            Vhat = [None] * 2  # quirk: the running max is never persisted (algorithms.py:176-177, 356-357)
+        else:
+            prob.get(_ffi.VHA, out=Vhat[0]); prob.get(_ffi.VHS, out=Vhat[1])
+    finally:
+        prob.close()
+    logger.info("Completed {0} iterations and {1} sub-iterations".format(done, [int(sub[0]), int(sub[1])]))
+    if check_convergence and not all(converged):
+        logger.warning("Solution did not converge")
+    conv = tuple(np.bool_(c) for c in converged) if check_convergence else (None,) * 2
+    return conv, M, V, Vhat
 
 
-def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, steps_g=None, Ls=None, update_order=None,
-          steps_g_update="steps_f", max_iter=1000, e_rel=1e-6, e_abs=0, callback=None):
-    raise NotImplementedError
+def _adaprox_callbacks(X, grad, step, prox, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter,
+                       prox_max_iter, M, V, Vhat, callback):
+    N = len(X)
+    if M is None:
+        M = tuple(np.zeros(x.shape, x.dtype) for x in X)
+    if V is None:
+        V = tuple(np.zeros(x.shape, x.dtype) for x in X)
+    if Vhat is None:
+        Vhat = [None] * N
+    Sub_iter = [0] * N
+    if callback is None:
+        callback = utils.NullCallback()
+    chains = [operators.describe(pj) if pj is not None else None for pj in prox]
+    b1 = np.asarray(b1, dtype=np.float64)
+    converged = (False,) * N
+    it = -1
+    for it in range(max_iter):
+        try:
+            callback(*X, it=it)
+            G = utils._as_tuple(grad(*X))
+            Alpha = utils._as_tuple(step(*X, it=it))
+            if check_convergence:
+                X_ = utils._copy_tuple(X)
+            for j in range(N):
+                Psi, psimax = _dev.adaprox_moments(scheme, G[j], M[j], V[j], Vhat[j], X[j], Alpha[j], b1[it],
+                                                   b1[it - 1], b2, eps, p, it + 1)
+                if prox[j] is not None:
+                    z = X[j].copy()
+                    gamma = Alpha[j] / psimax
+                    for tau in range(1, prox_max_iter + 1):
+                        if chains[j] is not None:
+                            z_, nd, nz = _dev.adaprox_sub(chains[j], z, X[j], Psi, Alpha[j], psimax)
+                        else:  # user prox: the argument is formed on the device, the callable runs on the host
+                            w, _, _ = _dev.adaprox_sub([], z, X[j], Psi, Alpha[j], psimax)
+                            z_ = np.asarray(prox[j](w, gamma), dtype=z.dtype)
+                            nd, nz = _dev.dot_diff(z_, z, z)[1], _dev.sumsq(z)
+                        conv = np.float32(nd) <= np.float32(e_rel[j] ** 2) * np.float32(nz)
+                        z = z_
+                        if conv:
+                            break
+                    logger.debug("Proximal sub-iterations for variable {}: {}".format(j, tau))
+                    Sub_iter[j] += tau
+                    X[j][:] = z
+            if check_convergence:
+                converged = []
+                for j in range(N):
+                    nd = _dev.dot_diff(X[j], X_[j], X[j])[1]
+                    converged.append(np.float32(nd) <= np.float32(e_rel[j] ** 2) * np.float32(_dev.sumsq(X[j])))
+                converged = tuple(converged)
+                if all(converged):
+                    break
+        except StopIteration:
+            break
+
+    logger.info("Completed {0} iterations and {1} sub-iterations".format(it + 1, Sub_iter))
+    if check_convergence and not all(converged):
+        logger.warning("Solution did not converge")
+    if not check_convergence:
+        converged = (None,) * N
+    return converged, M, V, Vhat
 
 
-def _bsdmm_nmf(Y, A, S, W, prox_A, prox_S, max_iter, e_rel, callback, **kw):
-    raise NotImplementedError
+# ------------------------------------------------------------------------------------------
+# ADMM family (L = identity)
+# ------------------------------------------------------------------------------------------
+def _no_L(L):
+    if L is None:
+        return
+    if hasattr(L, "__iter__") and not hasattr(L, "shape"):
+        for l in L:
+            _no_L(l)
+        return
+    raise NotImplementedError("linear operators L / Ls other than None (identity) are outside the B200 hot path "
+                              "(SURVEY.md section 8-f row 3)")
+
+
+def _step_g_of(step_f, N=1, M=1):
+    return step_f * 1 * N * M  # utils.py:279 with ||L||^2 = 1
+
+
+def _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g=True):
+    """utils.py:295-304 for L = identity.  Returns (LX, R, S, norms)."""
+    if chain_g is not None:
+        Znew = _dev.add(X, U)
+        operators._apply(Znew, step_g, chain_g)
+    else:
+        Znew = prox_g(_dev.add(X, U), step_g)
+    R, S, norms = _dev.admm_zu(X, Znew, Z, U, step_g, dual_uses_step_g)
+    return X, R, S, norms
+
+
+def _update_variables(X, Z, U, prox_f, step_f, prox_g, chain_g, step_g, dual_uses_step_g=True):
+    """utils.py:307-346 for L = identity.  Returns (LX, R, S, norms) -- lists in the multi-constraint case."""
+    if not hasattr(prox_g, "__iter__"):
+        if prox_g is not None:
+            X[:] = prox_f(_dev.admm_xarg(X, [Z], [U], [step_f / step_g]), step_f)
+            return _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g)
+        Xold = X.copy()
+        X[:] = prox_f(X, step_f)
+        Z[:] = X[:]
+        R = np.zeros(X.shape, dtype=X.dtype)
+        S = _dev.ew(_ffi.EW_SUB, X, Xold)[0][0].astype(X.dtype, copy=False)
+        nX = np.sqrt(np.float32(_dev.sumsq(X)))
+        norms = (nX, nX, np.sqrt(np.float32(_dev.sumsq(U))), np.float32(0), np.sqrt(np.float32(_dev.sumsq(S))))
+        return X, R, S, norms
+    m = len(prox_g)
+    X[:] = prox_f(_dev.admm_xarg(X, Z, U, [step_f / step_g[i] for i in range(m)]), step_f)
+    LX, R, S, norms = [None] * m, [None] * m, [None] * m, [None] * m
+    for i in range(m):
+        LX[i], R[i], S[i], norms[i] = _mm(X, Z[i], U[i], prox_g[i], chain_g[i], step_g[i], dual_uses_step_g)
+    return LX, R, S, norms
+
+
+def _constraint_convergence(size, norms, e_rel, e_abs):
+    """utils.py:349-391 for ||L|| = 1 from the five device norms of one constraint."""
+    lLX, lZ, lU, lR, lS = norms
+    e_pri = np.sqrt(size) * e_abs / 1 + e_rel * np.max([lLX, lZ])
+    e_dual = np.sqrt(size) * e_abs / 1 + e_rel * lU
+    return (lR <= e_pri) and (lS <= e_dual), (e_pri, e_dual, lR, lS)
+
+
+def _init_zu(X, m=None):
+    if m is None:
+        return X.copy(), np.zeros(X.shape, dtype=X.dtype)
+    return [X.copy() for _ in range(m)], [np.zeros(X.shape, dtype=X.dtype) for _ in range(m)]
+
+
+def _admm_device(X, b, step_value, chains, e_rel, e_abs, max_iter, dual_uses_step_g):
+    """Fused device loop (pmx_admm_run): the whole ADMM / SDMM iteration stays on the GPU."""
+    ctx = _ffi.context()
+    L = _ffi.lib()
+    o = _ffi.AdmmOpts()
+    o.n_g = len(chains)
+    for i, ch in enumerate(chains):
+        o.proxs_g[i] = _ffi.make_prox(ch)
+    o.e_rel, o.e_abs, o.dual_uses_step_g = float(e_rel), float(e_abs), int(dual_uses_step_g)
+    h = C.c_void_p()
+    _ffi.check(L.pmx_admm_create(ctx.handle, X.size, C.byref(o), C.byref(h)))
+    try:
+        x32 = np.ascontiguousarray(X, dtype=np.float32).reshape(-1)
+        b32 = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float32), X.shape)).reshape(-1)
+        vp = C.c_void_p
+        _ffi.check(L.pmx_admm_set(h, x32.ctypes.data_as(vp), b32.ctypes.data_as(vp)))
+        it, conv = C.c_int(0), C.c_int(0)
+        err = (C.c_double * 16)()
+        _ffi.check(L.pmx_admm_run(h, float(step_value), int(max_iter), C.byref(it), C.byref(conv), err))
+        _ffi.check(L.pmx_admm_get(h, x32.ctypes.data_as(vp)))
+        X[...] = x32.reshape(X.shape)
+    finally:
+        _ffi.check(L.pmx_admm_destroy(h))
+    errors = [tuple(X.dtype.type(err[4 * i + k]) for k in range(4)) for i in range(len(chains))]
+    return bool(conv.value), errors, it.value
+
+
+def _fusable_admm(X, prox_f, step_f, chains):
+    return (isinstance(prox_f, utils.LeastSquaresProx) and isinstance(step_f, utils.ConstantStep)
+            and np.ndim(step_f.value) == 0 and chains is not None and 1 <= len(chains) <= 4
+            and all(c is not None and all(o != _ffi.OP_UNITY for (o, _, _, _) in c) for c in chains)
+            and isinstance(X, np.ndarray))
+
+
+def admm(
+    X,
+    prox_f,
+    step_f,
+    prox_g=None,
+    step_g=None,
+    L=None,
+    e_rel=1e-6,
+    e_abs=0,
+    max_iter=1000,
+    callback=None,
+):
+    """Linearised ADMM with one constraint (algorithms.py:426-520).  Returns ``(converged, errors)``."""
+    _no_L(L)
+    chain_g = operators.describe(prox_g) if prox_g is not None else None
+
+    if (prox_g is not None and step_g is None and callback is None
+            and _fusable_admm(X, prox_f, step_f, [chain_g])):
+        # quirk kept: the tolerances of `admm` use the user's step_g (None) -> no division of U (algorithms.py:494-496)
+        converged, errors, logged = _admm_device(X, prox_f.b, step_f.value, [chain_g], e_rel, e_abs, max_iter,
+                                                 dual_uses_step_g=False)
+        logger.info("Completed {0} iterations".format(logged))
+        if not converged:
+            logger.warning("Solution did not converge")
+        return converged, errors[0]
+
+    Z, U = _init_zu(X)
+    it = 0
+    slack = 1.0
+    if callback is None:
+        callback = utils.NullCallback()
+    converged, error = False, None
+    while it < max_iter:
+        callback(X, it=it)
+        step_f_ = slack * step_f(X, it=it)
+        if prox_g is not None and step_g is None:
+            step_g_ = _step_g_of(step_f_)
+        else:
+            step_g_ = step_g
+        LX, R, S, norms = _update_variables(X, Z, U, prox_f, step_f_, prox_g, chain_g, step_g_,
+                                            dual_uses_step_g=step_g is not None)
+        converged, error = _constraint_convergence(X.size, norms, e_rel, e_abs)
+        if converged:
+            break
+        it += 1
+        if prox_g is not None:
+            if it > 1:
+                if (X == X_).all() and (R == R_).all():  # noqa: F821
+                    slack /= 2
+                    it = 0
+                    Z, U = _init_zu(X)
+                    logger.info("Restarting with step size slack = %.3f" % slack)
+            X_ = X.copy()
+            R_ = R
+
+    logger.info("Completed {0} iterations".format(it + 1))
+    if not converged:
+        logger.warning("Solution did not converge")
+    return converged, error
+
+
+def sdmm(
+    X,
+    prox_f,
+    step_f,
+    proxs_g=None,
+    steps_g=None,
+    Ls=None,
+    e_rel=1e-6,
+    e_abs=0,
+    max_iter=1000,
+    callback=None,
+):
+    """ADMM with several constraints on one variable (algorithms.py:523-650).  Returns ``converged``."""
+    if proxs_g is None or not hasattr(proxs_g, "__iter__"):
+        # fall back to admm, dropping e_abs like the reference (algorithms.py:568-579)
+        return admm(X, prox_f, step_f, prox_g=proxs_g, step_g=steps_g, L=Ls, e_rel=e_rel, max_iter=max_iter,
+                    callback=callback)
+    _no_L(Ls)
+    M = len(proxs_g)
+    chains = [operators.describe(pg) for pg in proxs_g]
+
+    if steps_g is None and callback is None and _fusable_admm(X, prox_f, step_f, chains):
+        converged, _, logged = _admm_device(X, prox_f.b, step_f.value, chains, e_rel, e_abs, max_iter,
+                                            dual_uses_step_g=True)
+        logger.info("Completed {0} iterations".format(logged))
+        if not converged:
+            logger.warning("Solution did not converge")
+        return converged
+
+    Z, U = _init_zu(X, M)
+    it = 0
+    slack = 1.0
+    if callback is None:
+        callback = utils.NullCallback()
+    converged = False
+    while it < max_iter:
+        callback(X, it=it)
+        step_f_ = slack * step_f(X, it=it)
+        if steps_g is None:
+            steps_g_ = [_step_g_of(step_f_, M=M) for i in range(M)]
+        else:
+            steps_g_ = steps_g
+        LX, R, S, norms = _update_variables(X, Z, U, prox_f, step_f_, proxs_g, chains, steps_g_)
+        converged = True
+        for i in range(M):
+            c, _ = _constraint_convergence(X.size, norms[i], e_rel, e_abs)
+            converged &= c
+        if converged:
+            break
+        it += 1
+        if it > 1:
+            if (X == X_).all() and all([(R[i] == R_[i]).all() for i in range(M)]):  # noqa: F821
+                slack /= 2
+                it = 0
+                Z, U = _init_zu(X, M)
+                logger.info("Restarting with step size slack = %.3f" % slack)
+        R_ = R
+        X_ = X.copy()
+
+    logger.info("Completed {0} iterations".format(it + 1))
+    if not converged:
+        logger.warning("Solution did not converge")
+    return converged
+
+
+def bsdmm(
+    X,
+    proxs_f,
+    steps_f_cb,
+    proxs_g=None,
+    steps_g=None,
+    Ls=None,
+    update_order=None,
+    steps_g_update="steps_f",
+    max_iter=1000,
+    e_rel=1e-6,
+    e_abs=0,
+    callback=None,
+):
+    """Block-SDMM: N variables x M_j constraints, Gauss-Seidel over the blocks (algorithms.py:653-850).
+
+    This is the callback loop (``proxs_f`` / ``steps_f_cb`` are user callables); ``nmf.nmf(..., algorithm=bsdmm)``
+    takes the fused device loop instead.  Returns the list ``converged``."""
+    N = len(X)
+    if proxs_g is None:
+        proxs_g = [None] * N
+    assert len(proxs_g) == N
+    steps_g_update = steps_g_update.lower()
+    assert steps_g_update in ["steps_f", "fixed", "relative"]
+    _no_L(Ls)
+    if steps_g is not None and steps_g_update != "steps_f":
+        raise NotImplementedError("steps_g_update='fixed'/'relative' with explicit steps_g (experts-only option)")
+
+    if np.isscalar(e_rel):
+        e_rel = [e_rel] * N
+    if np.isscalar(e_abs):
+        e_abs = [e_abs] * N
+    if update_order is None:
+        update_order = range(N)
+
+    proxs_g = list(proxs_g)
+    M = [0] * N
+    chains = [None] * N
+    for j in range(N):
+        if proxs_g[j] is not None:
+            if not hasattr(proxs_g[j], "__iter__"):
+                proxs_g[j] = [proxs_g[j]]
+            M[j] = len(proxs_g[j])
+            chains[j] = [operators.describe(pg) for pg in proxs_g[j]]
+
+    Z, U = [], []
+    for j in range(N):
+        z, u = _init_zu(X[j], None if proxs_g[j] is None else M[j])
+        Z.append(z)
+        U.append(u)
+
+    converged = [None] * N
+    it = 0
+    if callback is None:
+        callback = utils.NullCallback()
+
+    while it < max_iter:
+        callback(*X, it=it)
+        for j in update_order:
+            proxs_f_j = partial(proxs_f, j=j, Xs=X)
+            steps_f_j = steps_f_cb(X, j=j) * 1.0
+            if proxs_g[j] is None:
+                steps_g_j = None
+            else:
+                steps_g_j = [_step_g_of(steps_f_j, N=N, M=M[j]) for i in range(M[j])]
+            LX, R, S, norms = _update_variables(X[j], Z[j], U[j], proxs_f_j, steps_f_j, proxs_g[j], chains[j],
+                                                steps_g_j)
+            if proxs_g[j] is None:
+                converged[j], _ = _constraint_convergence(X[j].size, norms, e_rel[j], e_abs[j])
+            else:
+                ok = True
+                for i in range(M[j]):
+                    c, _ = _constraint_convergence(X[j].size, norms[i], e_rel[j], e_abs[j])
+                    ok &= c
+                converged[j] = ok
+        it += 1
+        if all(converged):
+            break
+
+    logger.info("Completed {0} iterations".format(it))
+    if not all(converged):
+        logger.warning("Solution did not converge")
+    return converged
+
+
+def _bsdmm_nmf(Y, A, S, W, prox_A, prox_S, max_iter, e_rel, callback, proxs_g=None, e_abs=0, **kw):
+    """nmf.nmf(..., algorithm=bsdmm): the closures of nmf.py:181-193 driven through algorithms.py:653-850,
+    fused on the device (gradient kernel + Lipschitz steps + ADMM variable updates per block)."""
+    from . import nmf as _nmf
+
+    _nmf._check_W(W)
+    unsupported = set(kw) - {"steps_g", "Ls", "update_order", "steps_g_update"}
+    if unsupported:
+        raise TypeError("bsdmm() got unexpected keyword arguments %s" % sorted(unsupported))
+    if kw.get("steps_g") is not None or kw.get("Ls") is not None or kw.get("update_order") is not None \
+            or kw.get("steps_g_update", "steps_f").lower() != "steps_f":
+        raise NotImplementedError("nmf(..., algorithm=bsdmm) on the device supports the defaults of steps_g, Ls, "
+                                  "update_order and steps_g_update only")
+    if proxs_g is None:
+        proxs_g = [None, None]
+    assert len(proxs_g) == 2
+    direct = _describe_all([prox_A, prox_S])
+    g_chains = []
+    for pg in proxs_g:
+        if pg is None:
+            g_chains.append([])
+            continue
+        if not hasattr(pg, "__iter__"):
+            pg = [pg]
+        d = _describe_all(list(pg))
+        if d is None or len(d) > 4:
+            direct = None
+            break
+        g_chains.append(d)
+    if direct is None or any(o == _ffi.OP_UNITY for ch in direct for (o, _, _, _) in ch):
+        raise NotImplementedError("nmf(..., algorithm=bsdmm): constraints must be built-in proximal operators "
+                                  "(prox_unity only inside proxs_g)")
+    if np.isscalar(e_rel):
+        e_rel = [e_rel] * 2
+    if np.isscalar(e_abs):
+        e_abs = [e_abs] * 2
+    X = [A, S]
+    prob = _nmf.Problem(Y, A, S)
+    try:
+        prob.bsdmm_begin(direct[0], direct[1], g_chains[0], g_chains[1], e_rel, e_abs)
+        done, converged = 0, [False, False]
+        if callback is None:
+            done, converged = prob.bsdmm_run(max_iter)
+        else:
+            for it in range(max_iter):
+                callback(*X, it=it)
+                n, converged = prob.bsdmm_run(1)
+                done += n
+                _writeback(prob, X)
+                if all(converged):
+                    break
+        _writeback(prob, X)
+    finally:
+        prob.close()
+    logger.info("Completed {0} iterations".format(done))
+    if not all(converged):
+        logger.warning("Solution did not converge")
+    return converged

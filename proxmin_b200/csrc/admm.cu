@@ -1,16 +1,322 @@
-// temporary stubs (replaced by the real ADMM / adaprox / bsdmm loops)
-#include "common.cuh"
-#define STUB { pmx_set_error("not implemented yet"); return PMX_ERR_UNSUPPORTED; }
-extern "C" {
-int pmx_nmf_adaprox_begin(pmx_nmf*, const pmx_adaprox_opts*) STUB
-int pmx_nmf_adaprox_run(pmx_nmf*, int, const double*, const double*, int*, int*, int*, long long*, long long*) STUB
-int pmx_nmf_bsdmm_begin(pmx_nmf*, const pmx_bsdmm_opts*) STUB
-int pmx_nmf_bsdmm_run(pmx_nmf*, int, int*, int*, int*) STUB
-int pmx_admm_create(pmx_ctx*, size_t, const pmx_admm_opts*, pmx_admm**) STUB
-int pmx_admm_destroy(pmx_admm*) STUB
-int pmx_admm_set(pmx_admm*, const float*, const float*) STUB
-int pmx_admm_get(pmx_admm*, float*) STUB
-int pmx_admm_init_zu(pmx_admm*) STUB
-int pmx_admm_step(pmx_admm*, float, int*, int*, double*) STUB
-int pmx_admm_run(pmx_admm*, float, int, int*, int*, double*) STUB
+// Linearised ADMM / SDMM on one block with L = identity, fully fused:
+//   utils.py:307-346  update_variables (X step through prox_f, then do_the_mm per constraint)
+//   utils.py:295-304  do_the_mm        (Z' = prox_g(X + U), R = X - Z', S = -(Z' - Z)/step_g, U += R)
+//   utils.py:349-391  get_variable_errors / check_constraint_convergence (5 norms per constraint)
+//   algorithms.py:478-514, 603-644  iteration counter, stall detection and the halved-slack restart
+// One elementwise kernel per iteration reads X, b, Z_i, U_i and writes X, Z_i, U_i (7 fp32 streams for
+// one constraint = the 28 bytes/element of SURVEY 8-d); all norms and the "nothing changed" test are
+// fused into it, and a one-thread kernel keeps the iteration / restart state machine on the device.
+// The arithmetic uses explicit round-to-nearest intrinsics in the reference's operation order (no FMA
+// contraction), so X, Z, U are bit-identical to NumPy's fp32 results.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace {
+
+constexpr int kT = 256;
+constexpr int MAXG = 4;
+
+struct admm_ctl {
+  int done, it, converged, reinit, restarts, max_iter;
+  int changed_x, changed_r;
+  float slack;
+  float pad;
+  double norms[MAXG][5];   // |LX|^2, |Z|^2, |U(/step_g)|^2, |R|^2, |S|^2   (after the pass)
+  double errors[MAXG][4];  // e_pri, e_dual, |R|, |S|
+};
+
+struct PassArgs {
+  float* X;
+  const float* b;
+  float* Z[MAXG];
+  float* U[MAXG];
+  size_t n;
+  int n_g;
+  ProxChain chain[MAXG];
+  double step_base;   // step_f(X, it) of the caller; multiplied by ctl->slack when use_slack
+  int use_slack;
+  int dual_uses_step_g;
+  admm_ctl* ctl;
+};
+
+__global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
+  admm_ctl* ctl = a.ctl;
+  if (ctl->done) return;
+  const bool reinit = ctl->reinit != 0;   // utils.py:244-254 folded into the pass: Z = X, U = 0
+  // scalar recipe in double, then one rounding to fp32 (NumPy weak-scalar promotion of Python floats)
+  const double sf_d = a.use_slack ? (double)ctl->slack * a.step_base : a.step_base;   // algorithms.py:482
+  const double sg_d = sf_d * 1 * 1 * (a.n_g > 1 ? a.n_g : 1);                         // utils.py:279
+  const float sf = (float)sf_d;
+  const float sg = (float)sg_d;
+  const float ratio = (float)(sf_d / sg_d);     // step_f / step_g   (utils.py:316,333)
+  const float cS = (float)(-1.0 / sg_d);        // -1 / step_g       (utils.py:300)
+  float acc[MAXG][5];
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) acc[i][q] = 0.f;
+  int ch_x = 0, ch_r = 0;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n; idx += (size_t)gridDim.x * blockDim.x) {
+    const float x = a.X[idx];
+    float z[MAXG], u[MAXG];
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < a.n_g) {
+        z[i] = reinit ? x : a.Z[i][idx];
+        u[i] = reinit ? 0.f : a.U[i][idx];
+      }
+    // dX = sum_i step_f/step_g_i (X - Z_i + U_i)    (left-to-right like np.sum over the list, utils.py:331-337)
+    float dX = __fmul_rn(ratio, __fadd_rn(__fsub_rn(x, z[0]), u[0]));
+#pragma unroll
+    for (int i = 1; i < MAXG; ++i)
+      if (i < a.n_g) dX = __fadd_rn(dX, __fmul_rn(ratio, __fadd_rn(__fsub_rn(x, z[i]), u[i])));
+    const float xa = __fsub_rn(x, dX);
+    // prox_f(Xa, step_f) = Xa - step_f (Xa - b)       (utils.LeastSquaresProx, README.md:82-84)
+    const float xn = __fsub_rn(xa, __fmul_rn(sf, __fsub_rn(xa, a.b[idx])));
+    a.X[idx] = xn;
+    ch_x |= (xn != x) && !(xn != xn && x != x);
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < a.n_g) {
+        const float zn = chain_segment(a.chain[i], 0, a.chain[i].n, __fadd_rn(xn, u[i]), sg);  // utils.py:297
+        const float r = __fsub_rn(xn, zn);                                                      // utils.py:299
+        const float s = __fmul_rn(cS, __fsub_rn(zn, z[i]));                                     // utils.py:300
+        const float un = __fadd_rn(u[i], r);                                                    // utils.py:303
+        a.Z[i][idx] = zn;
+        a.U[i][idx] = un;
+        const float r_prev = __fsub_rn(x, z[i]);  // the R of the previous pass (same fp32 subtraction)
+        ch_r |= (r != r_prev);
+        const float uq = a.dual_uses_step_g ? __fdiv_rn(un, sg) : un;                           // utils.py:359-362
+        acc[i][0] = fmaf(xn, xn, acc[i][0]);
+        acc[i][1] = fmaf(zn, zn, acc[i][1]);
+        acc[i][2] = fmaf(uq, uq, acc[i][2]);
+        acc[i][3] = fmaf(r, r, acc[i][3]);
+        acc[i][4] = fmaf(s, s, acc[i][4]);
+      }
+  }
+  // block reduction: norms and the two change flags
+  __shared__ float red[kT / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      if (i >= a.n_g) continue;   // block-uniform
+      float v = acc[i][q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      __syncthreads();
+      if (lane == 0) red[w] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < kT / 32; ++k) t += red[k];
+        atomicAdd(&ctl->norms[i][q], (double)t);
+      }
+    }
+  const int any_x = __syncthreads_or(ch_x);
+  const int any_r = __syncthreads_or(ch_r);
+  if (threadIdx.x == 0) {
+    if (any_x) ctl->changed_x = 1;
+    if (any_r) ctl->changed_r = 1;
+  }
 }
+
+// convergence test + iteration / restart state machine (algorithms.py:494-514)
+__global__ void k_admm_finalize(admm_ctl* ctl, int n_g, double n_elems, float e_rel, float e_abs, int manage) {
+  if (ctl->done) return;
+  bool all = true;
+  for (int i = 0; i < n_g; ++i) {
+    const float lLX = sqrtf((float)ctl->norms[i][0]);
+    const float lZ = sqrtf((float)ctl->norms[i][1]);
+    const float lU = sqrtf((float)ctl->norms[i][2]);
+    const float lR = sqrtf((float)ctl->norms[i][3]);
+    const float lS = sqrtf((float)ctl->norms[i][4]);
+    // np.sqrt(p) * e_abs is float64 in the reference, the e_rel product fp32 (utils.py:357-362)
+    const double e_pri = sqrt(n_elems) * (double)e_abs + (double)(e_rel * fmaxf(lLX, lZ));
+    const double e_dual = sqrt(n_elems) * (double)e_abs + (double)(e_rel * lU);
+    ctl->errors[i][0] = e_pri;
+    ctl->errors[i][1] = e_dual;
+    ctl->errors[i][2] = lR;
+    ctl->errors[i][3] = lS;
+    all = all && ((double)lR <= e_pri) && ((double)lS <= e_dual);                                            // utils.py:390
+    for (int q = 0; q < 5; ++q) ctl->norms[i][q] = 0.0;
+  }
+  const bool stalled = !ctl->changed_x && !ctl->changed_r;
+  ctl->changed_x = 0;
+  ctl->changed_r = 0;
+  ctl->converged = all ? 1 : 0;
+  ctl->reinit = 0;
+  if (!manage) {
+    ctl->restarts = stalled ? 1 : 0;   // step mode: report "nothing changed" to the host
+    return;
+  }
+  if (all) {
+    ctl->done = 1;
+    return;
+  }
+  ctl->it += 1;
+  if (ctl->it > 1 && stalled) {        // algorithms.py:503-512: halve the slack, restart
+    ctl->slack *= 0.5f;
+    ctl->it = 0;
+    ctl->reinit = 1;
+    ctl->restarts += 1;
+    if (ctl->restarts > 64) ctl->done = 1;
+  }
+  if (ctl->it >= ctl->max_iter) ctl->done = 1;   // `while it < max_iter`
+}
+
+}  // namespace
+
+struct pmx_admm {
+  pmx_ctx* ctx;
+  size_t n;
+  pmx_admm_opts opts;
+  float *X, *b;
+  float* Z[MAXG];
+  float* U[MAXG];
+  admm_ctl* ctl;
+  admm_ctl* h_ctl;
+};
+
+static int admm_pull(pmx_admm* h) {
+  PMX_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(admm_ctl), cudaMemcpyDeviceToHost, h->ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return PMX_OK;
+}
+
+static int admm_enqueue(pmx_admm* h, double step_base, int use_slack, int manage) {
+  pmx_ctx* ctx = h->ctx;
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = h->X;
+  a.b = h->b;
+  a.n = h->n;
+  a.n_g = h->opts.n_g;
+  for (int i = 0; i < h->opts.n_g; ++i) {
+    a.Z[i] = h->Z[i];
+    a.U[i] = h->U[i];
+    a.chain[i] = make_chain(&h->opts.proxs_g[i]);
+  }
+  a.step_base = step_base;
+  a.use_slack = use_slack;
+  a.dual_uses_step_g = h->opts.dual_uses_step_g;
+  a.ctl = h->ctl;
+  long long blocks = (long long)((h->n + kT - 1) / kT);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_admm_pass<<<(int)blocks, kT, 0, ctx->stream>>>(a);
+  PMX_LAUNCHED(ctx);
+  k_admm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, h->opts.n_g, (double)h->n, h->opts.e_rel, h->opts.e_abs, manage);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "admm pass");
+}
+
+extern "C" {
+
+int pmx_admm_create(pmx_ctx* ctx, size_t n, const pmx_admm_opts* opts, pmx_admm** out) {
+  PMX_REQUIRE(ctx && opts && out, "NULL argument");
+  PMX_REQUIRE(opts->n_g >= 1 && opts->n_g <= MAXG, "1..4 constraints are supported by the fused ADMM loop");
+  for (int i = 0; i < opts->n_g; ++i)
+    for (int k = 0; k < opts->proxs_g[i].n_ops; ++k)
+      if (opts->proxs_g[i].ops[k].op == PMX_OP_UNITY) {
+        pmx_set_error("prox_unity inside a vector ADMM constraint needs a global sum; use the callback loop");
+        return PMX_ERR_UNSUPPORTED;
+      }
+  pmx_admm* h = new pmx_admm();
+  memset(h, 0, sizeof(*h));
+  h->ctx = ctx;
+  h->n = n;
+  h->opts = *opts;
+  PMX_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(float) * (n ? n : 1);
+  PMX_CUDA(cudaMalloc((void**)&h->X, bytes));
+  PMX_CUDA(cudaMalloc((void**)&h->b, bytes));
+  for (int i = 0; i < opts->n_g; ++i) {
+    PMX_CUDA(cudaMalloc((void**)&h->Z[i], bytes));
+    PMX_CUDA(cudaMalloc((void**)&h->U[i], bytes));
+  }
+  PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(admm_ctl)));
+  PMX_CUDA(cudaMallocHost((void**)&h->h_ctl, sizeof(admm_ctl)));
+  *out = h;
+  return pmx_admm_init_zu(h);
+}
+
+int pmx_admm_destroy(pmx_admm* h) {
+  if (!h) return PMX_OK;
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaFree(h->X);
+  cudaFree(h->b);
+  for (int i = 0; i < MAXG; ++i) {
+    if (h->Z[i]) cudaFree(h->Z[i]);
+    if (h->U[i]) cudaFree(h->U[i]);
+  }
+  cudaFree(h->ctl);
+  cudaFreeHost(h->h_ctl);
+  delete h;
+  return PMX_OK;
+}
+
+int pmx_admm_set(pmx_admm* h, const float* host_X, const float* host_b) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  if (host_X) PMX_CHECK(pmx_h2d(h->ctx, h->X, host_X, sizeof(float) * h->n));
+  if (host_b) PMX_CHECK(pmx_h2d(h->ctx, h->b, host_b, sizeof(float) * h->n));
+  return PMX_OK;
+}
+
+int pmx_admm_get(pmx_admm* h, float* host_X) {
+  PMX_REQUIRE(h && host_X, "NULL argument");
+  return pmx_d2h(h->ctx, host_X, h->X, sizeof(float) * h->n);
+}
+
+int pmx_admm_init_zu(pmx_admm* h) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  admm_ctl c;
+  memset(&c, 0, sizeof(c));
+  c.slack = 1.0f;
+  c.reinit = 1;  // the next pass treats Z = X, U = 0 (utils.py:244-254)
+  c.max_iter = 1 << 30;
+  memcpy(h->h_ctl, &c, sizeof(c));
+  PMX_CUDA(cudaMemcpyAsync(h->ctl, h->h_ctl, sizeof(admm_ctl), cudaMemcpyHostToDevice, h->ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return PMX_OK;
+}
+
+int pmx_admm_step(pmx_admm* h, double step_f, int* converged, int* stalled, double* errors) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  PMX_CHECK(admm_enqueue(h, step_f, 0, 0));
+  PMX_CHECK(admm_pull(h));
+  if (converged) *converged = h->h_ctl->converged;
+  if (stalled) *stalled = h->h_ctl->restarts;
+  if (errors) memcpy(errors, h->h_ctl->errors, sizeof(double) * 4 * h->opts.n_g);
+  return PMX_OK;
+}
+
+int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, int* converged, double* errors) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  PMX_REQUIRE(max_iter >= 0, "max_iter must be >= 0");
+  PMX_CHECK(pmx_admm_init_zu(h));
+  h->h_ctl->max_iter = max_iter;
+  if (max_iter == 0) h->h_ctl->done = 1;
+  PMX_CUDA(cudaMemcpyAsync(h->ctl, h->h_ctl, sizeof(admm_ctl), cudaMemcpyHostToDevice, h->ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  const int batch = 16;
+  long long guard = 0;
+  while (!h->h_ctl->done) {
+    for (int i = 0; i < batch; ++i) PMX_CHECK(admm_enqueue(h, step_f, 1, 1));
+    PMX_CHECK(admm_pull(h));
+    if (++guard > (1LL << 26)) break;
+  }
+  if (iters_logged) *iters_logged = h->h_ctl->it + 1;   // "Completed it + 1 iterations" (algorithms.py:516)
+  if (converged) *converged = h->h_ctl->converged;
+  if (errors) memcpy(errors, h->h_ctl->errors, sizeof(double) * 4 * h->opts.n_g);
+  if (h->h_ctl->restarts > 64) {
+    pmx_set_error("ADMM restarted more than 64 times without progress");
+    return PMX_ERR_UNSUPPORTED;
+  }
+  return PMX_OK;
+}
+
+}  // extern "C"

@@ -75,6 +75,10 @@ int pmx_ctx_destroy(pmx_ctx* ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
   cudaFreeHost(ctx->h_flags);
+  if (ctx->prof_ev) {
+    for (int i = 0; i < 2 * PMX_PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+    delete[] ctx->prof_ev;
+  }
   delete ctx;
   return PMX_OK;
 }
@@ -89,6 +93,31 @@ int pmx_ctx_sync(pmx_ctx* ctx) {
 int pmx_ctx_launch_count(pmx_ctx* ctx, long long* count) {
   PMX_REQUIRE(ctx && count, "NULL argument");
   *count = ctx->launches;
+  return PMX_OK;
+}
+
+int pmx_ctx_profile(pmx_ctx* ctx, int enable) {
+  PMX_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (enable && !ctx->prof_ev) {
+    ctx->prof_ev = new cudaEvent_t[2 * PMX_PROF_MAX];
+    for (int i = 0; i < 2 * PMX_PROF_MAX; ++i) PMX_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+  }
+  ctx->profile = enable ? 1 : 0;
+  ctx->prof_n = 0;
+  return PMX_OK;
+}
+
+int pmx_ctx_profile_read(pmx_ctx* ctx, float* total_ms, int* launches) {
+  PMX_REQUIRE(ctx && total_ms && launches, "NULL argument");
+  PMX_CUDA(cudaStreamSynchronize(ctx->stream));
+  float tot = 0.f;
+  for (int i = 0; i < ctx->prof_n; ++i) {
+    float ms = 0.f;
+    PMX_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = ctx->prof_n;
   return PMX_OK;
 }
 

@@ -46,7 +46,7 @@ struct pmx_ctl {
   int sub_tau;       // adaprox: sub-iterations used by the current block in this iteration
   int sub_parity;    // adaprox: which z buffer holds the result
   long long sub_total[2];
-  double norms[8];   // [0..2] block A: |dX|^2, |X|^2, |Xprev|^2 ; [3..5] block S ; [6] loss ; [7] spare
+  double norms[16];  // [0..2] block A: |dX|^2, |X|^2, |Xprev|^2 ; [3..5] block S ; [6] loss ; [8..10] adaprox sub-iteration
   float step[2];     // 1/lambda_max for A and S (algorithms.py:106)
   float lip[2];      // lambda_max(S S^T), lambda_max(A^T A)
   float psi_max[2];  // adaprox: max(Psi) per block (algorithms.py:384)
@@ -63,6 +63,10 @@ struct pmx_ctx {
   // NCCL (dlopen'ed lazily)
   void* nccl_comm;
   int world, rank;
+  // optional per-launch timing of the dominant kernel (bench.py roofline leg)
+  int profile;                 // 0 off, 1 on
+  int prof_n;                  // recorded launches
+  cudaEvent_t* prof_ev;        // 2 * PMX_PROF_MAX events (start, stop)
   // scratch
   int* h_flags;          // pinned host mirror for polled device flags
   char dev_name[128];
@@ -72,5 +76,6 @@ struct pmx_ctx {
 static inline int pmx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #define PMX_LAUNCHED(ctx) ((ctx)->launches++)
+#define PMX_PROF_MAX 4096
 
 int pmx_check_launch(pmx_ctx* ctx, const char* what);

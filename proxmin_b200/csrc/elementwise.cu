@@ -7,7 +7,7 @@
 // along the contiguous dimension) and 128-bit where the layout allows.
 #include <cuda_bf16.h>
 
-#include "prox.cuh"
+#include "kernels.h"
 
 namespace {
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ float transform(const UpdIO& io, size_t i, int r, int
   const float s = step_at(io.step, r, c);
   if (IN == IN_PGM) {  // algorithms.py:108  _X[j] - T[j]*S[j]*G[j]
     pstep = s;
-    return io.Xin[i] - s * io.G[i];
+    return __fsub_rn(io.Xin[i], __fmul_rn(s, io.G[i]));  // two roundings like NumPy, no FMA contraction
   }
   if (IN == IN_ADASUB) {  // algorithms.py:384,387  z - gamma/Alpha * Psi * (z - X), prox step gamma
     const float gamma = s / io.psimax[0];
@@ -333,26 +333,6 @@ int launch_split_bf16(pmx_ctx* ctx, const float* X, int rows, int cols, void* hi
 // adaprox moment update (algorithms.py:147-245) fused with the step X -= Alpha*Phi/Psi (:378),
 // the copy z = X (:383) and the block-wide max(Psi) (:384).
 // =========================================================================================
-struct AdaArgs {
-  const float* G;
-  float* M;
-  float* V;
-  float* Vhat;   // may be null (quirk: then the running max is never applied, algorithms.py:176-177)
-  float* X;
-  float* Psi;    // out
-  float* Z;      // out: copy of the stepped X
-  float* Xold;   // optional out: X before the step (convergence test, algorithms.py:371-372)
-  float* psimax; // out (atomicMax on the bit pattern; Psi >= 0)
-  const int* done;
-  size_t n;
-  int rows, cols;
-  StepSpec alpha;
-  int scheme;
-  double b1, b1_prev;  // b1 is a float64 array in the reference (algorithms.py:327-328): M is formed in double
-  float b2, eps, p;
-  int t;  // it + 1
-};
-
 __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
   if (a.done && *a.done) return;
   float pm = 0.f;

@@ -8,23 +8,26 @@
 // A and S arrive pre-split (k_split_bf16); R is split in the epilogue registers.
 //
 // Tiling: a tile is 128 rows (m) x 128 columns (n) of Y; K <= 64 (operands zero-padded to 64).
-// The tile sequence is stripe-major (all m-blocks of a 128-column stripe are consecutive) and is
-// cut into gridDim.x contiguous, equally long ranges -- one persistent CTA per SM -- so the load is
-// balanced to within one tile.  Inside a stripe segment G_S^T accumulates in TMEM across the
-// m-blocks; the 128 x 64 G_A partial of every tile is flushed with vector red.add into the
-// (L2-resident) G_A buffer.
+// The tile sequence is m-block major (all 128-column stripes of a 128-row block are consecutive) and
+// is cut into gridDim.x contiguous, equally long ranges -- one persistent CTA per SM -- so the load is
+// balanced to within one tile.  Inside a row segment G_A accumulates in TMEM across the stripes and is
+// flushed once; the 128 x 64 G_S^T partial of every tile is flushed with red.add into G_S, lanes
+// running along n so that every warp-level reduction is one fully coalesced 128-byte line.
 //
 // Shared memory (all operands are "panels": rows of 128 bytes, 128B-swizzled in 8-row atoms, which
 // the same bytes can be read as a K-major or an MN-major UMMA operand):
-//   S_hi,S_lo  [2 n-panels][64 k-rows][128B]   32 KB   per stripe        (TMA)
-//   A_hi,A_lo  [128 m-rows][128B] x 2 slots    64 KB   per tile          (TMA)
+//   S_hi,S_lo  [2 n-panels][64 k-rows][128B] x 2 slots  64 KB   per tile      (TMA)
+//   A_hi,A_lo  [128 m-rows][128B]              32 KB   per row segment   (TMA)
 //   R_hi,R_lo  [2 n-panels][128 m-rows][128B]  64 KB   per tile          (epilogue writes)
 //   Y ring     4 x [128 m-rows][32 fp32]       64 KB   4 sub-tiles/tile  (TMA)
-// TMEM (512 columns): residual accumulator 2 x 128, G_A accumulator 2 x 64, G_S^T accumulator 64.
+// TMEM (512 columns): residual accumulator 2 x 128, G_S^T accumulator 2 x 64, G_A accumulator 64.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM -> registers -> residual -> SMEM, gradient flushes).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (TMEM -> registers -> residual -> SMEM, gradient flushes); two warps share
+// each TMEM lane quarter and split the column chunks so that every SM sub-partition has two
+// epilogue warps to hide the TMEM / shared-memory latencies.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "grad_umma.h"
 #include "kernels.h"
@@ -38,23 +41,22 @@ constexpr uint32_t PANEL_S = 64 * 128;    // bytes of one S panel (64 k-rows)
 constexpr uint32_t PANEL_R = 128 * 128;   // bytes of one R / A panel (128 m-rows)
 
 // shared-memory map (offsets from the 1024-aligned base)
-constexpr uint32_t OFF_S_HI = 0;
-constexpr uint32_t OFF_S_LO = OFF_S_HI + 2 * PANEL_S;
-constexpr uint32_t OFF_A = OFF_S_LO + 2 * PANEL_S;          // slot s: hi at OFF_A + s*2*PANEL_R, lo right after
-constexpr uint32_t OFF_R_HI = OFF_A + 4 * PANEL_R;
+constexpr uint32_t OFF_S = 0;                               // slot s: hi at OFF_S + s*4*PANEL_S, lo 2 panels later
+constexpr uint32_t OFF_A = OFF_S + 8 * PANEL_S;             // A_hi, then A_lo (one m-block at a time)
+constexpr uint32_t OFF_R_HI = OFF_A + 2 * PANEL_R;
 constexpr uint32_t OFF_R_LO = OFF_R_HI + 2 * PANEL_R;
 constexpr uint32_t OFF_Y = OFF_R_LO + 2 * PANEL_R;
 constexpr uint32_t OFF_BAR = OFF_Y + Y_STAGES * PANEL_R;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
 
 enum {  // mbarrier indices
-  B_S_FULL = 0, B_S_EMPTY, B_A_FULL, B_A_EMPTY = B_A_FULL + 2, B_Y_FULL = B_A_EMPTY + 2,
+  B_A_FULL = 0, B_A_EMPTY, B_S_FULL, B_S_EMPTY = B_S_FULL + 2, B_Y_FULL = B_S_EMPTY + 2,
   B_Y_EMPTY = B_Y_FULL + Y_STAGES, B_ACC_FULL = B_Y_EMPTY + Y_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2,
-  B_R_FULL = B_ACC_EMPTY + 2, B_R_EMPTY, B_GA_FULL, B_GA_EMPTY = B_GA_FULL + 2, B_GS_FULL = B_GA_EMPTY + 2,
-  B_GS_EMPTY, B_COUNT
+  B_R_FULL = B_ACC_EMPTY + 2, B_R_EMPTY, B_GS_FULL, B_GS_EMPTY = B_GS_FULL + 2, B_GA_FULL = B_GS_EMPTY + 2,
+  B_GA_EMPTY, B_COUNT
 };
 
-constexpr uint32_t TM_ACC = 0, TM_GA = 256, TM_GS = 384;   // TMEM column offsets
+constexpr uint32_t TM_ACC = 0, TM_GS = 256, TM_GA = 384;   // TMEM column offsets
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,15 +139,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 
 struct Params {
   int M, N, K;
-  int MB;                 // m-blocks per stripe
-  long long total_tiles;  // stripes * MB
+  int NS;                 // 128-column stripes per m-block row
+  long long total_tiles;  // m-blocks * NS
   float* GA;
   float* GS;
   double* loss;
   const int* done;
+  int ablate;             // debug/timing only (env PMX_ABLATE): bit0 no MMA1, 1 no MMA2, 2 no MMA3, 3 no Y read, 4 no R store, 5 no G_S flush, 6 no epilogue math
 };
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAhi,
             const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmShi,
             const __grid_constant__ CUtensorMap tmSlo, Params p) {
@@ -160,17 +166,18 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // tile sequence: m-block major (all 128-column stripes of one 128-row block are consecutive)
   const long long g_begin = (long long)blockIdx.x * p.total_tiles / gridDim.x;
   const long long g_end = (long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       uint32_t count = 1;
-      if (i >= B_Y_EMPTY && i < B_Y_EMPTY + Y_STAGES) count = 4;
-      if (i == B_ACC_EMPTY || i == B_ACC_EMPTY + 1) count = 4;
-      if (i == B_R_FULL) count = 4;
-      if (i == B_GA_EMPTY || i == B_GA_EMPTY + 1) count = 4;
-      if (i == B_GS_EMPTY) count = 4;
+      if (i >= B_Y_EMPTY && i < B_Y_EMPTY + Y_STAGES) count = NUM_EPI_WARPS / 2;   // one column-chunk group
+      if (i == B_ACC_EMPTY || i == B_ACC_EMPTY + 1) count = NUM_EPI_WARPS;
+      if (i == B_R_FULL) count = NUM_EPI_WARPS;
+      if (i == B_GS_EMPTY || i == B_GS_EMPTY + 1) count = NUM_EPI_WARPS;
+      if (i == B_GA_EMPTY) count = NUM_EPI_WARPS;
       mbar_init(bar(i), count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,36 +191,37 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  auto first_in_seg = [&](long long g) { return g == g_begin || (g % p.MB) == 0; };
-  auto last_in_seg = [&](long long g) { return g == g_end - 1 || (g % p.MB) == p.MB - 1; };
+  auto first_in_seg = [&](long long g) { return g == g_begin || (g % p.NS) == 0; };
+  auto last_in_seg = [&](long long g) { return g == g_end - 1 || (g % p.NS) == p.NS - 1; };
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       uint32_t t = 0, seg = 0;
       for (long long g = g_begin; g < g_end; ++g, ++t) {
-        const int stripe = (int)(g / p.MB), mb = (int)(g % p.MB);
+        const int mb = (int)(g / p.NS), stripe = (int)(g % p.NS);
         const int m0 = mb * TILE_M, n0 = stripe * TILE_N;
         const uint32_t slot = t & 1;
-        // A tile (hi, lo): 2 x 16 KB
-        mbar_wait(bar(B_A_EMPTY + slot), ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(bar(B_A_FULL + slot), 2 * PANEL_R);
-        tma_load_2d(base + OFF_A + slot * 2 * PANEL_R, &tmAhi, 0, m0, bar(B_A_FULL + slot));
-        tma_load_2d(base + OFF_A + slot * 2 * PANEL_R + PANEL_R, &tmAlo, 0, m0, bar(B_A_FULL + slot));
+        // S stripe tile (hi, lo): 4 boxes of 64 k-rows x 64 columns
+        mbar_wait(bar(B_S_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(B_S_FULL + slot), 4 * PANEL_S);
+        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
+        tma_load_2d(s_hi, &tmShi, n0, 0, bar(B_S_FULL + slot));
+        tma_load_2d(s_hi + PANEL_S, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot));
+        tma_load_2d(s_lo, &tmSlo, n0, 0, bar(B_S_FULL + slot));
+        tma_load_2d(s_lo + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot));
         // Y sub-tiles
         for (int q = 0; q < 4; ++q) {
           mbar_wait(bar(B_Y_EMPTY + q), (t & 1) ^ 1);
           mbar_expect_tx(bar(B_Y_FULL + q), PANEL_R);
           tma_load_2d(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q));
         }
-        // S stripe (after the prefetch of this tile's A and Y so that the stripe switch does not stall them)
+        // A tile of the m-block (after the prefetch above so that a segment switch does not stall it)
         if (first_in_seg(g)) {
-          mbar_wait(bar(B_S_EMPTY), (seg & 1) ^ 1);
-          mbar_expect_tx(bar(B_S_FULL), 4 * PANEL_S);
-          tma_load_2d(base + OFF_S_HI, &tmShi, n0, 0, bar(B_S_FULL));
-          tma_load_2d(base + OFF_S_HI + PANEL_S, &tmShi, n0 + 64, 0, bar(B_S_FULL));
-          tma_load_2d(base + OFF_S_LO, &tmSlo, n0, 0, bar(B_S_FULL));
-          tma_load_2d(base + OFF_S_LO + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL));
+          mbar_wait(bar(B_A_EMPTY), (seg & 1) ^ 1);
+          mbar_expect_tx(bar(B_A_FULL), 2 * PANEL_R);
+          tma_load_2d(base + OFF_A, &tmAhi, 0, m0, bar(B_A_FULL));
+          tma_load_2d(base + OFF_A + PANEL_R, &tmAlo, 0, m0, bar(B_A_FULL));
           ++seg;
         }
       }
@@ -224,26 +232,28 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);  // A tile K-major, S tile MN-major
       constexpr uint32_t ID_GA = make_idesc(128, 64, 0, 0);    // R K-major, S tile K-major
       constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);    // R^T (MN-major), A tile MN-major
-      uint32_t seg_full = 0;  // S segments consumed so far (parity source for s_full)
+      uint32_t seg_full = 0;
+      const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
 
       auto issue_residual = [&](long long g, uint32_t t) {
         const uint32_t slot = t & 1;
-        mbar_wait(bar(B_A_FULL + slot), (t >> 1) & 1);
+        mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);
         if (first_in_seg(g)) {
-          mbar_wait(bar(B_S_FULL), seg_full & 1);
+          mbar_wait(bar(B_A_FULL), seg_full & 1);
           ++seg_full;
         }
         mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_hi = base + OFF_A + slot * 2 * PANEL_R, a_lo = a_hi + PANEL_R;
+        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
         const uint32_t d = tmem + TM_ACC + slot * 128;
         // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16)
         const uint32_t a_src[3] = {a_hi, a_hi, a_lo};
-        const uint32_t s_src[3] = {base + OFF_S_HI, base + OFF_S_LO, base + OFF_S_HI};
+        const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
 #pragma unroll
         for (int term = 0; term < 3; ++term)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (p.ablate & 1) continue;
             const uint64_t ad = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major
             const uint64_t bd = make_desc(s_src[term] + ks * 2048, PANEL_S, 1024);      // MN-major: LBO = next 64 n
             umma_bf16(d, ad, bd, ID_RES, (term | ks) ? 1u : 0u);
@@ -255,91 +265,83 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       if (g_begin < g_end) issue_residual(g_begin, 0);
       for (long long g = g_begin; g < g_end; ++g, ++t) {
         const bool has_next = g + 1 < g_end;
-        if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a stripe
+        if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a segment
         const uint32_t slot = t & 1;
         mbar_wait(bar(B_R_FULL), t & 1);
-        mbar_wait(bar(B_GA_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         const bool first = first_in_seg(g);
-        if (first) mbar_wait(bar(B_GS_EMPTY), (seg & 1) ^ 1);
+        if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_hi = base + OFF_A + slot * 2 * PANEL_R, a_lo = a_hi + PANEL_R;
         const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
-        const uint32_t s_hi = base + OFF_S_HI, s_lo = base + OFF_S_LO;
-        {  // G_A[m, k] = R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps)
-          const uint32_t d = tmem + TM_GA + slot * 64;
+        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
+        {  // G_A[m, k] += R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps); accumulates over the segment
+          const uint32_t d = tmem + TM_GA;
           const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
           const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
 #pragma unroll
           for (int term = 0; term < 3; ++term)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
+              if (p.ablate & 2) continue;
               const uint64_t ad = make_desc(r_src[term] + (ks >> 2) * PANEL_R + (ks & 3) * 32, 16, 1024);  // K-major
               const uint64_t bd = make_desc(s_src[term] + (ks >> 2) * PANEL_S + (ks & 3) * 32, 16, 1024);  // K-major
-              umma_bf16(d, ad, bd, ID_GA, (term | ks) ? 1u : 0u);
+              umma_bf16(d, ad, bd, ID_GA, (!first || (term | ks)) ? 1u : 0u);
             }
         }
-        {  // G_S^T[n, k] += R^T A : M = n (128), N = k (64), K = m (128: 8 k-steps)
-          const uint32_t d = tmem + TM_GS;
+        {  // G_S^T[n, k] = R^T A : M = n (128), N = k (64), K = m (128: 8 k-steps); one accumulator per tile
+          const uint32_t d = tmem + TM_GS + slot * 64;
           const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
           const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
 #pragma unroll
           for (int term = 0; term < 3; ++term)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
+              if (p.ablate & 4) continue;
               const uint64_t ad = make_desc(r_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major: LBO = next 64 n
               const uint64_t bd = make_desc(a_src[term] + ks * 2048, 1024, 1024);     // MN-major, one 64-wide atom
-              umma_bf16(d, ad, bd, ID_GS, (!first || (term | ks)) ? 1u : 0u);
+              umma_bf16(d, ad, bd, ID_GS, (term | ks) ? 1u : 0u);
             }
         }
         tc_commit(bar(B_R_EMPTY));
-        tc_commit(bar(B_A_EMPTY + slot));
-        tc_commit(bar(B_GA_FULL + slot));
+        tc_commit(bar(B_S_EMPTY + slot));
+        tc_commit(bar(B_GS_FULL + slot));
         if (last_in_seg(g)) {
-          tc_commit(bar(B_GS_FULL));
-          tc_commit(bar(B_S_EMPTY));
+          tc_commit(bar(B_GA_FULL));
+          tc_commit(bar(B_A_EMPTY));
           ++seg;
         }
-        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new stripe: needs the new S tile
+        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A tile
       }
     }
   } else if (warp >= 4) {
-    // ============================== epilogue ==============================
+    // ============================== epilogue (8 warps) ==============================
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;         // column-chunk group: chunks q with (q & 1) == grp
     const int row = q4 * 32 + lane;          // row of the tile (m for acc / G_A, n for G_S^T)
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     float loss_part = 0.f;
     uint32_t t = 0, seg = 0;
-    long long pending_g = -1;   // tile whose G_A accumulator still has to be flushed
+    long long pending_g = -1;   // tile whose G_S^T accumulator still has to be flushed
     uint32_t pending_t = 0;
 
-    auto flush_ga = [&](long long g, uint32_t tt) {
+    // G_S^T[n, k] -> G_S[k, n]: for a fixed k the 32 lanes of a warp hit 32 consecutive floats (one line)
+    auto flush_gs = [&](long long g, uint32_t tt) {
       const uint32_t slot = tt & 1;
-      const int m = (int)(g % p.MB) * TILE_M + row;
-      mbar_wait(bar(B_GA_FULL + slot), (tt >> 1) & 1);
+      const int n = (int)(g % p.NS) * TILE_N + row;
+      mbar_wait(bar(B_GS_FULL + slot), (tt >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + TM_GA + slot * 64 + half * 32, v);
-        tmem_ld_wait();
-        if (m < p.M) {
-          float* dst = p.GA + (size_t)m * p.K + half * 32;
-          if ((p.K & 3) == 0) {
-#pragma unroll
-            for (int k = 0; k < 32; k += 4)
-              if (half * 32 + k < p.K)
-                red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
-                           __uint_as_float(v[k + 3]));
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (half * 32 + k < p.K) atomicAdd(dst + k, __uint_as_float(v[k]));
-          }
-        }
-      }
+      uint32_t v[32];
+      tmem_ld32(lane_addr + TM_GS + slot * 64 + grp * 32, v);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_GA_EMPTY + slot));
+      if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
+      if (n < p.N && !(p.ablate & 32)) {
+        float* dst = p.GS + (size_t)(grp * 32) * p.N + n;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (grp * 32 + k < p.K) atomicAdd(dst + (size_t)k * p.N, __uint_as_float(v[k]));
+      }
     };
 
     for (long long g = g_begin; g < g_end; ++g, ++t) {
@@ -348,7 +350,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       mbar_wait(bar(B_R_EMPTY), (t & 1) ^ 1);   // MMAs of the previous tile no longer read R
       tc_fence_after();
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = qq * 2 + grp;
         mbar_wait(bar(B_Y_FULL + q), t & 1);
         uint32_t acc[32];
         tmem_ld32(lane_addr + TM_ACC + slot * 128 + q * 32, acc);
@@ -356,12 +359,15 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         const uint8_t* yrow = base_ptr + OFF_Y + q * PANEL_R + row * 128;
         float4 yv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) yv[c] = *reinterpret_cast<const float4*>(yrow + ((c ^ (row & 7)) << 4));
+        for (int c = 0; c < 8; ++c)
+          yv[c] = (p.ablate & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                 : *reinterpret_cast<const float4*>(yrow + ((c ^ (row & 7)) << 4));
         tmem_ld_wait();
         const float* yf = reinterpret_cast<const float*>(yv);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
+          if (p.ablate & 64) { hi[j >> 1] = acc[j]; lo[j >> 1] = acc[j + 1]; continue; }
           const float r0 = __uint_as_float(acc[j]) - yf[j];          // nmf.py:40  (A S - Y)
           const float r1 = __uint_as_float(acc[j + 1]) - yf[j + 1];
           loss_part = fmaf(r0, r0, loss_part);
@@ -377,6 +383,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         uint8_t* rl = base_ptr + OFF_R_LO + (q >> 1) * PANEL_R + row * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          if (p.ablate & 16) continue;
           const int chunk = ((q & 1) * 4 + c) ^ (row & 7);
           *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
           *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
@@ -391,31 +398,37 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         mbar_arrive(bar(B_ACC_EMPTY + slot));
         mbar_arrive(bar(B_R_FULL));
       }
-      // deferred flush of the previous tile's G_A (its MMAs finished while we built this R)
-      if (pending_g >= 0) flush_ga(pending_g, pending_t);
+      // deferred flush of the previous tile's G_S^T (its MMAs finished while we built this R)
+      if (pending_g >= 0) flush_gs(pending_g, pending_t);
       pending_g = g;
       pending_t = t;
       if (last_in_seg(g)) {
-        flush_ga(g, t);  // waits for this tile's MMAs
+        flush_gs(g, t);  // waits for this tile's MMAs
         pending_g = -1;
-        // G_S^T[n, k] -> G_S[k, n]: coalesced along n across the warp
-        mbar_wait(bar(B_GS_FULL), seg & 1);
+        // G_A[m, k] of the whole segment: once per m-block row and CTA
+        mbar_wait(bar(B_GA_FULL), seg & 1);
         tc_fence_after();
-        const int n = (int)(g / p.MB) * TILE_N + row;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + TM_GS + half * 32, v);
-          tmem_ld_wait();
-          if (n < p.N) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (half * 32 + k < p.K) atomicAdd(p.GS + (size_t)(half * 32 + k) * p.N + n, __uint_as_float(v[k]));
-          }
-        }
+        const int m = (int)(g / p.NS) * TILE_M + row;
+        uint32_t v[32];
+        tmem_ld32(lane_addr + TM_GA + grp * 32, v);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_GS_EMPTY));
+        if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
+        if (m < p.M) {
+          float* dst = p.GA + (size_t)m * p.K + grp * 32;
+          if ((p.K & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              if (grp * 32 + k < p.K)
+                red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                           __uint_as_float(v[k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (grp * 32 + k < p.K) atomicAdd(dst + k, __uint_as_float(v[k]));
+          }
+        }
         ++seg;
       }
     }
@@ -527,11 +540,21 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   if (loss) PMX_CHECK(launch_zero(ctx, ctx->stream, reinterpret_cast<float*>(loss), 2, done));
   Params p;
   p.M = pl->M; p.N = pl->N; p.K = pl->K;
-  p.MB = pl->Mp / TILE_M;
-  p.total_tiles = (long long)(pl->Np / TILE_N) * p.MB;
+  p.NS = pl->Np / TILE_N;
+  p.total_tiles = (long long)(pl->Mp / TILE_M) * p.NS;
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
+  {
+    const char* ab = getenv("PMX_ABLATE");
+    p.ablate = ab ? atoi(ab) : 0;
+  }
   int grid = (int)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
-  k_grad_umma<<<grid, 256, SMEM_BYTES, ctx->stream>>>(pl->tmY, pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+  const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;
+  if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
+  k_grad_umma<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(pl->tmY, pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+  if (prof) {
+    PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream));
+    ctx->prof_n++;
+  }
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_grad_umma");
 }

@@ -2,8 +2,6 @@
 #pragma once
 #include "prox.cuh"
 
-struct AdaArgs;
-
 int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done);
 int launch_extrapolate(pmx_ctx* ctx, const float* X, const float* Xold, float* Xe, size_t n, float omega,
                        const int* done);
@@ -14,3 +12,41 @@ int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int col
 int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which);
 int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done);
+
+// solver_kernels.cu
+int launch_diff_norms(pmx_ctx* ctx, const float* X, const float* Xold, size_t n, double* norms, const int* done);
+int launch_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* out, const int* done);
+int apply_chain_general(pmx_ctx* ctx, const ProxChain& ch, float* X, int rows, int cols, const StepSpec& step,
+                        double* sums_scratch, const int* done);
+int launch_alpha_means(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* sums, float* alpha,
+                       const int* done);
+int launch_sub_begin(pmx_ctx* ctx, pmx_ctl* ctl, int block);
+int launch_sub_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2, int max_tau);
+int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, size_t n, pmx_ctl* ctl, int block);
+int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, int check);
+int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const float* G, float* const* Z, float* const* U,
+                       float* T, double* sums_scratch, int rows, int cols, int n_g, const ProxChain& direct,
+                       const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs);
+int launch_bsdmm_iter_finalize(pmx_ctx* ctx, pmx_ctl* ctl);
+
+// elementwise.cu: adaprox moment update
+struct AdaArgs {
+  const float* G;
+  float* M;
+  float* V;
+  float* Vhat;   // may be null (quirk: then the running max is never applied, algorithms.py:176-177)
+  float* X;
+  float* Psi;    // out
+  float* Z;      // out: copy of the stepped X
+  float* Xold;   // optional out: X before the step (convergence test, algorithms.py:371-372)
+  float* psimax; // out (atomicMax on the bit pattern; Psi >= 0)
+  const int* done;
+  size_t n;
+  int rows, cols;
+  StepSpec alpha;
+  int scheme;
+  double b1, b1_prev;  // b1 is a float64 array in the reference (algorithms.py:327-328): M is formed in double
+  float b2, eps, p;
+  int t;  // it + 1
+};
+int launch_adaprox_moments(pmx_ctx* ctx, const AdaArgs& a);

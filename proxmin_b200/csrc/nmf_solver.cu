@@ -329,6 +329,214 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
   return PMX_OK;
 }
 
+// ------------------------------------------------------------------ adaprox (algorithms.py:248-423)
+int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
+  PMX_REQUIRE(h && opts, "NULL argument");
+  PMX_REQUIRE(opts->scheme >= PMX_ADAM && opts->scheme <= PMX_RADAM, "unknown adaprox scheme");
+  if (h->ctx->world > 1) {
+    pmx_set_error("adaprox on a column-sharded problem is not implemented yet (single GPU only)");
+    return PMX_ERR_UNSUPPORTED;
+  }
+  h->ada = *opts;
+  h->chA = make_chain(&opts->prox_A);
+  h->chS = make_chain(&opts->prox_S);
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  const size_t big = mk > kn ? mk : kn;
+  float** bufs[] = {&h->MA, &h->VA, &h->MS, &h->VS};
+  const size_t sizes[] = {mk, mk, kn, kn};
+  for (int i = 0; i < 4; ++i) {
+    if (!*bufs[i]) PMX_CHECK(alloc_f(bufs[i], sizes[i]));
+    PMX_CUDA(cudaMemsetAsync(*bufs[i], 0, sizeof(float) * sizes[i], h->ctx->stream));   // algorithms.py:348-355
+  }
+  if (opts->has_vhat) {
+    if (!h->VhA) PMX_CHECK(alloc_f(&h->VhA, mk));
+    if (!h->VhS) PMX_CHECK(alloc_f(&h->VhS, kn));
+  }
+  if (!h->Psi) PMX_CHECK(alloc_f(&h->Psi, big));
+  if (!h->Z0) PMX_CHECK(alloc_f(&h->Z0, big));
+  if (!h->Z1) PMX_CHECK(alloc_f(&h->Z1, big));
+  if (!h->alphaA) PMX_CHECK(alloc_f(&h->alphaA, h->K));
+  if (!h->alphaS) PMX_CHECK(alloc_f(&h->alphaS, h->K));
+  if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
+  h->ada_it = 0;
+  PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  return PMX_OK;
+}
+
+static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
+  pmx_ctx* ctx = h->ctx;
+  pmx_ctl* ctl = h->ctl;
+  const pmx_adaprox_opts& o = h->ada;
+  const int rows = j == 0 ? h->M : h->K, cols = j == 0 ? h->K : h->N;
+  const size_t n = (size_t)rows * cols;
+  float* X = j == 0 ? h->A : h->S;
+  StepSpec alpha;
+  memset(&alpha, 0, sizeof(alpha));
+  alpha.scale = 1.f;
+  if (o.step_mode == 0) {   // nmf.py:91-93: A gets a K-vector (per column), S a K x 1 column (per row)
+    alpha.ptr = j == 0 ? h->alphaA : h->alphaS;
+    alpha.mode = j == 0 ? 2 : 3;
+  } else {
+    alpha.mode = 0;
+    alpha.value = j == 0 ? o.alpha_A : o.alpha_S;
+  }
+  PMX_CHECK(launch_sub_begin(ctx, ctl, j));
+  AdaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = j == 0 ? h->GA : h->GS;
+  a.M = j == 0 ? h->MA : h->MS;
+  a.V = j == 0 ? h->VA : h->VS;
+  a.Vhat = o.has_vhat ? (j == 0 ? h->VhA : h->VhS) : nullptr;
+  a.X = X;
+  a.Psi = h->Psi;
+  a.Z = h->Z0;
+  a.Xold = o.check_convergence ? (j == 0 ? h->A_old : h->S_old) : nullptr;
+  a.psimax = &ctl->psi_max[j];
+  a.done = &ctl->done;
+  a.n = n; a.rows = rows; a.cols = cols;
+  a.alpha = alpha;
+  a.scheme = o.scheme;
+  a.b1 = b1; a.b1_prev = b1_prev; a.b2 = o.b2; a.eps = o.eps; a.p = o.p;
+  a.t = it + 1;
+  PMX_CHECK(launch_adaprox_moments(ctx, a));
+  const bool has_prox = j == 0 ? o.has_prox_A : o.has_prox_S;
+  if (!has_prox) return PMX_OK;   // algorithms.py:380
+  const ProxChain& ch = j == 0 ? h->chA : h->chS;
+  const float e = j == 0 ? o.e_rel_A : o.e_rel_S;
+  const float e2 = (float)((double)e * (double)e);
+  // proximal sub-iterations (algorithms.py:386-393): enqueue two at a time, then poll the device flag
+  int enq = 0;
+  while (enq < o.prox_max_iter) {
+    for (int rep = 0; rep < 2 && enq < o.prox_max_iter; ++rep, ++enq) {
+      UpdIO io;
+      memset(&io, 0, sizeof(io));
+      const bool odd = enq & 1;
+      io.Xin = odd ? h->Z1 : h->Z0;
+      io.Xprev = io.Xin;
+      io.Xout = odd ? h->Z0 : h->Z1;
+      io.X0 = X;
+      io.G = h->Psi;
+      io.psimax = &ctl->psi_max[j];
+      io.norms = &ctl->norms[8];
+      io.done = &ctl->done;
+      io.done2 = &ctl->sub_done;
+      io.rows = rows; io.cols = cols;
+      io.step = alpha;
+      PMX_CHECK(launch_update(ctx, IN_ADASUB, ch, io));
+      PMX_CHECK(launch_sub_finalize(ctx, ctl, e2, o.prox_max_iter));
+    }
+    PMX_CHECK(pull_ctl(h));
+    if (h->h_ctl->sub_done || h->h_ctl->done) break;
+  }
+  PMX_CHECK(launch_sub_commit(ctx, X, h->Z0, h->Z1, n, ctl, j));
+  return PMX_OK;
+}
+
+int pmx_nmf_adaprox_run(pmx_nmf* h, int n_iter, const double* b1, const double* b1_prev, int* iters_done, int* conv_A,
+                        int* conv_S, long long* sub_A, long long* sub_S) {
+  PMX_REQUIRE(h && b1 && b1_prev, "NULL argument");
+  pmx_ctx* ctx = h->ctx;
+  const pmx_adaprox_opts& o = h->ada;
+  PMX_CHECK(pull_ctl(h));
+  const int it0 = h->h_ctl->it;
+  for (int i = 0; i < n_iter; ++i) {
+    if (h->h_ctl->done) break;
+    const int it = h->ada_it;
+    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));   // algorithms.py:369
+    if (o.step_mode == 0) {                                                                     // algorithms.py:370
+      PMX_CHECK(launch_alpha_means(ctx, h->A, h->M, h->K, 0, h->bs_norms, h->alphaA, &h->ctl->done));
+      PMX_CHECK(launch_alpha_means(ctx, h->S, h->K, h->N, 1, h->bs_norms + 128, h->alphaS, &h->ctl->done));
+    }
+    PMX_CHECK(adaprox_block(h, 0, it, b1[i], b1_prev[i]));
+    PMX_CHECK(adaprox_block(h, 1, it, b1[i], b1_prev[i]));
+    if (o.check_convergence) {   // algorithms.py:403-410
+      PMX_CHECK(launch_diff_norms(ctx, h->A, h->A_old, (size_t)h->M * h->K, &h->ctl->norms[0], &h->ctl->done));
+      PMX_CHECK(launch_diff_norms(ctx, h->S, h->S_old, (size_t)h->K * h->N, &h->ctl->norms[3], &h->ctl->done));
+    }
+    const float eA = o.e_rel_A, eS = o.e_rel_S;
+    PMX_CHECK(launch_adaprox_finalize(ctx, h->ctl, (float)((double)eA * eA), (float)((double)eS * eS), o.check_convergence));
+    h->ada_it += 1;
+    PMX_CHECK(pull_ctl(h));   // the sub-iteration loop syncs anyway; keeps `done` current
+  }
+  PMX_CHECK(pull_ctl(h));
+  if (iters_done) *iters_done = h->h_ctl->it - it0;
+  if (conv_A) *conv_A = h->h_ctl->conv[0];
+  if (conv_S) *conv_S = h->h_ctl->conv[1];
+  if (sub_A) *sub_A = h->h_ctl->sub_total[0];
+  if (sub_S) *sub_S = h->h_ctl->sub_total[1];
+  return PMX_OK;
+}
+
+// ------------------------------------------------------------------ bsdmm (algorithms.py:653-850 via nmf.py:178-203)
+int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
+  PMX_REQUIRE(h && opts, "NULL argument");
+  PMX_REQUIRE(opts->n_g_A >= 0 && opts->n_g_A <= 4 && opts->n_g_S >= 0 && opts->n_g_S <= 4, "0..4 constraints per block");
+  if (h->ctx->world > 1) {
+    pmx_set_error("bsdmm on a column-sharded problem is not implemented yet (single GPU only)");
+    return PMX_ERR_UNSUPPORTED;
+  }
+  h->bs = *opts;
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  const size_t big = mk > kn ? mk : kn;
+  for (int j = 0; j < 2; ++j) {
+    const int ng = j == 0 ? opts->n_g_A : opts->n_g_S;
+    const size_t n = j == 0 ? mk : kn;
+    const float* X = j == 0 ? h->A : h->S;
+    for (int i = 0; i < ng; ++i) {   // Z_ji = X_j.copy(), U_ji = 0   (algorithms.py:787-790, utils.py:244-254)
+      if (!h->Zg[j][i]) PMX_CHECK(alloc_f(&h->Zg[j][i], n));
+      if (!h->Ug[j][i]) PMX_CHECK(alloc_f(&h->Ug[j][i], n));
+      PMX_CUDA(cudaMemcpyAsync(h->Zg[j][i], X, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->ctx->stream));
+      PMX_CUDA(cudaMemsetAsync(h->Ug[j][i], 0, sizeof(float) * n, h->ctx->stream));
+    }
+  }
+  if (!h->Z0) PMX_CHECK(alloc_f(&h->Z0, big));
+  if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
+  PMX_CUDA(cudaMemsetAsync(h->bs_norms, 0, sizeof(double) * 256, h->ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  h->bs_it = 0;
+  return PMX_OK;
+}
+
+int pmx_nmf_bsdmm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* conv_S) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  pmx_ctx* ctx = h->ctx;
+  const pmx_bsdmm_opts& o = h->bs;
+  PMX_CHECK(pull_ctl(h));
+  const int it0 = h->h_ctl->it;
+  ProxChain dA = make_chain(&o.prox_A), dS = make_chain(&o.prox_S);
+  ProxChain gA[4], gS[4];
+  for (int i = 0; i < 4; ++i) {
+    gA[i] = make_chain(i < o.n_g_A ? &o.proxs_g_A[i] : nullptr);
+    gS[i] = make_chain(i < o.n_g_S ? &o.proxs_g_S[i] : nullptr);
+  }
+  double* sums = h->bs_norms + 64;   // scratch for UNITY sums (up to 128 doubles)
+  for (int i = 0; i < n_iter; ++i) {
+    if (h->h_ctl->done) break;
+    // block A (Gauss-Seidel: uses the current S), then block S with the updated A  (algorithms.py:805-839)
+    PMX_CHECK(nmf_steps(h, h->A, h->S, true, false));
+    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
+    PMX_CHECK(nmf_steps_join(h));
+    PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 0, h->A, h->GA, h->Zg[0], h->Ug[0], h->Z0, sums, h->M, h->K, o.n_g_A, dA,
+                                 gA, &h->ctl->step[0], h->bs_norms, o.e_rel_A, o.e_abs_A));
+    PMX_CHECK(nmf_steps(h, h->A, h->S, false, true));
+    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
+    PMX_CHECK(nmf_steps_join(h));
+    PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 1, h->S, h->GS, h->Zg[1], h->Ug[1], h->Z0, sums, h->K, h->N, o.n_g_S, dS,
+                                 gS, &h->ctl->step[1], h->bs_norms + 32, o.e_rel_S, o.e_abs_S));
+    PMX_CHECK(launch_bsdmm_iter_finalize(ctx, h->ctl));
+    if ((i + 1) % 8 == 0) PMX_CHECK(pull_ctl(h));
+  }
+  PMX_CHECK(pull_ctl(h));
+  if (iters_done) *iters_done = h->h_ctl->it - it0;
+  if (conv_A) *conv_A = h->h_ctl->conv[0];
+  if (conv_S) *conv_S = h->h_ctl->conv[1];
+  if (h->h_ctl->nonfinite) {
+    pmx_set_error("Gram matrix contains infs or NaNs (iteration %d)", h->h_ctl->it);
+    return PMX_ERR_NONFINITE;
+  }
+  return PMX_OK;
+}
+
 int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, int M, int N, int K, float* G_A,
                  float* G_S, double* loss_or_null, int kernel) {
   PMX_REQUIRE(ctx && Y && A && S && G_A && G_S, "NULL argument");

@@ -69,7 +69,7 @@ __device__ __forceinline__ float prox_elem(float x, int op, float t) {
 // apply the elementwise ops [a, b) of the chain
 __device__ __forceinline__ float chain_segment(const ProxChain& c, int a, int b, float x, float step) {
   for (int i = a; i < b; ++i) {
-    float t = c.rel[i] ? c.thr[i] * step : c.thr[i];  // operators.py:4-14 in fp32 (NumPy weak-scalar rule)
+    float t = c.rel[i] ? __fmul_rn(c.thr[i], step) : c.thr[i];  // operators.py:4-14 in fp32 (NumPy weak-scalar rule)
     x = prox_elem(x, c.op[i], t);
   }
   return x;

@@ -116,3 +116,169 @@ def test_oracle_agrees_live(product):
     b = cases.nmf_pgm_ragged(product)
     assert_close(b["A"], a["A"], 1e-4, "A")
     assert_close(b["S"], a["S"], 1e-4, "S")
+
+
+# ---------------------------------------------------------------- generic solvers with user callables
+@pytest.mark.parametrize("name", ["parabola_circle", "parabola_line"])
+def test_parabola_known_answers(product, name):
+    """examples/parabola.py through every solver: user grad/step/prox callables on the host, library
+    arithmetic on the device (fp32): end points within 2e-5 of the reference's fp64 run."""
+    want = load_golden(name)
+    got = cases.CASES[name](product)
+    for k in want:
+        assert np.allclose(got[k], want[k], rtol=0, atol=2e-5), (k, got[k], want[k])
+
+
+# ---------------------------------------------------------------- adaprox / bsdmm on the NMF path
+def test_nmf_adaprox_amsgrad(product):
+    want = load_golden("nmf_adaprox_amsgrad")
+    got = cases.nmf_adaprox_amsgrad(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert list(got["sub_iterations"]) == list(want["sub_iterations"])
+    # adaprox normalises the gradient by sqrt(V): ~100x more sensitive than PGM (SURVEY 7.3); bound 5e-4
+    assert_close(got["A"], want["A"], 5e-4, "A")
+    assert_close(got["S"], want["S"], 5e-4, "S")
+    assert_close(got["M_A"], want["M_A"], 5e-3, "M_A")
+    assert_close(got["V_S"], want["V_S"], 5e-3, "V_S")
+
+
+def test_nmf_adaprox_amsgrad_unity(product):
+    want = load_golden("nmf_adaprox_amsgrad_unity")
+    got = cases.nmf_adaprox_amsgrad_unity(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    sub_g, sub_w = list(got["sub_iterations"]), list(want["sub_iterations"])
+    assert all(abs(a - b) <= max(2, 0.02 * b) for a, b in zip(sub_g, sub_w)), (sub_g, sub_w)
+    assert_close(got["A"], want["A"], 1e-3, "A")
+    assert_close(got["S"], want["S"], 1e-3, "S")
+
+
+def test_nmf_adaprox_schemes(product):
+    want = load_golden("nmf_adaprox_schemes")
+    got = cases.nmf_adaprox_schemes(product)
+    for scheme in ["adam", "nadam", "padam", "adamx"]:
+        assert int(got[scheme + "_iterations"]) == int(want[scheme + "_iterations"]), scheme
+        assert_close(got[scheme + "_A"], want[scheme + "_A"], 1e-3, scheme + ":A")
+        assert_close(got[scheme + "_S"], want[scheme + "_S"], 1e-3, scheme + ":S")
+
+
+def test_nmf_bsdmm(product):
+    want = load_golden("nmf_bsdmm")
+    got = cases.nmf_bsdmm(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert np.array_equal(got["converged"], want["converged"])
+    assert_close(got["A"], want["A"], 2e-4, "A")
+    assert_close(got["S"], want["S"], 2e-4, "S")
+
+
+# ---------------------------------------------------------------- ADMM / SDMM
+def test_admm_lasso_callback_loop(product):
+    """plain closures for prox_f / step_f: callback loop, ADMM variable updates on the device"""
+    want = load_golden("admm_lasso")
+    got = cases.admm_lasso(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert bool(got["converged"]) == bool(want["converged"])
+    assert_close(got["X"], want["X"], 1e-6, "X")
+    assert_same_support(got["X"], want["X"], "X")
+
+
+def test_admm_lasso_fused_bit_exact(product):
+    """LeastSquaresProx + ConstantStep + built-in prox_g: the fused device loop.  The kernel keeps NumPy's
+    operation order without FMA contraction, so X is bit-identical to the reference's fp32 result."""
+    from functools import partial
+
+    import proxmin_b200 as pmx
+    from proxmin_b200 import workloads
+
+    want = load_golden("admm_lasso")
+    b, X = workloads.cfg4(10_000, seed=7)
+    conv, err = pmx.admm(X, pmx.utils.LeastSquaresProx(b), pmx.utils.ConstantStep(0.5),
+                         prox_g=partial(pmx.prox_soft, thresh=0.5), max_iter=200, e_rel=1e-6)
+    n, _ = product.iterations()
+    assert n == int(want["iterations"])
+    assert bool(conv) == bool(want["converged"])
+    assert np.array_equal(X, want["X"])
+    assert np.array_equal(np.signbit(X), np.signbit(want["X"]))
+    assert np.allclose(np.array(err, dtype=np.float64), want["errors"], rtol=1e-5)
+
+
+def test_sdmm_lasso(product):
+    from functools import partial
+
+    import proxmin_b200 as pmx
+    from proxmin_b200 import workloads
+
+    want = load_golden("sdmm_lasso_plus")
+    got = cases.sdmm_lasso_plus(product)          # callback loop
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert_close(got["X"], want["X"], 1e-6, "X")
+    b, X = workloads.cfg4(10_000, seed=8)          # fused device loop
+    conv = pmx.sdmm(X, pmx.utils.LeastSquaresProx(b), pmx.utils.ConstantStep(0.5),
+                    proxs_g=[partial(pmx.prox_soft, thresh=0.5), pmx.prox_plus], max_iter=100, e_rel=1e-5)
+    n, _ = product.iterations()
+    assert n == int(want["iterations"])
+    assert bool(conv) == bool(want["converged"])
+    assert np.array_equal(X, want["X"])
+
+
+# ---------------------------------------------------------------- tcgen05 kernel vs the SIMT kernel
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 512, 8), (300, 1000, 20), (77, 204, 5), (1024, 2048, 64)])
+def test_tcgen05_gradient_matches_fp64(shape):
+    """3xBF16-split tensor-core GEMMs: gradients within 2e-5 (relative Frobenius) of an fp64 evaluation"""
+    import ctypes as C
+
+    from proxmin_b200 import _ffi
+
+    M, N, K = shape
+    rng = np.random.default_rng(123)
+    A = rng.random((M, K), dtype=np.float32)
+    S = rng.random((K, N), dtype=np.float32)
+    Y = (rng.random((M, K), dtype=np.float32) @ rng.random((K, N), dtype=np.float32)).astype(np.float32)
+    R = A.astype(np.float64) @ S.astype(np.float64) - Y
+    ctx = _ffi.context()
+    dY, dA, dS = ctx.upload(Y), ctx.upload(A), ctx.upload(S)
+    dGA, dGS, dl = ctx.malloc(4 * M * K), ctx.malloc(4 * K * N), ctx.malloc(16)
+    try:
+        _ffi.check(_ffi.lib().pmx_nmf_grad(ctx.handle, dY, dA, dS, M, N, K, dGA, dGS, dl, 2))
+        GA, GS, loss = np.empty((M, K), np.float32), np.empty((K, N), np.float32), np.empty(2, np.float64)
+        ctx.d2h(GA, dGA)
+        ctx.d2h(GS, dGS)
+        ctx.d2h(loss, dl)
+    finally:
+        for p in (dY, dA, dS, dGA, dGS, dl):
+            ctx.free(p)
+    assert rel_fro(GA, R @ S.T.astype(np.float64)) < 2e-5
+    assert rel_fro(GS, A.T.astype(np.float64) @ R) < 2e-5
+    assert abs(loss[0] - 0.5 * (R ** 2).sum()) <= 5e-6 * 0.5 * (R ** 2).sum()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (8192 x 65536, K = 64): size-independent properties of the fused path.
+
+    * linearity of the gradient in Y:  G(Y1) + G(Y2) - G(0) == G(Y1 + Y2)   (G is affine in Y)
+    * prox_unity_plus idempotence: column sums of S are 1 and S >= 0 after every iteration
+    * the loss decreases monotonically under the Lipschitz steps"""
+    import proxmin_b200 as pmx
+    from proxmin_b200 import _ffi
+    from proxmin_b200 import nmf as pnmf
+
+    M, N, K = 8192, 65536, 64
+    rng = np.random.default_rng(5)
+    A0 = rng.random((M, K), dtype=np.float32)
+    S0 = rng.random((K, N), dtype=np.float32)
+    Y = A0[:, :8] @ rng.random((8, N), dtype=np.float32)
+    prob = pnmf.Problem(Y, A0, S0)
+    try:
+        chain_A = [(_ffi.OP_PLUS, 0, 0, 0.0)]
+        chain_S = [(_ffi.OP_PLUS, 0, 0, 0.0), (_ffi.OP_UNITY, 0, 0, 0.0)]
+        prob.pgm_begin(chain_A, chain_S, e_rel=(0.0, 0.0))
+        losses = [prob.loss()]
+        for _ in range(3):
+            prob.pgm_run(2)
+            losses.append(prob.loss())
+        S = prob.get(_ffi.S)
+        A = prob.get(_ffi.A)
+    finally:
+        prob.close()
+    assert np.all(np.diff(losses) < 0), losses
+    assert S.min() >= 0 and A.min() >= 0
+    assert np.allclose(S.sum(axis=0), 1.0, atol=1e-5)

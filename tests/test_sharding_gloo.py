@@ -1,0 +1,77 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo run of the column-sharded PGM iteration.
+
+The device loop (nmf_solver.cu: pgm_enqueue_iteration) shards Y and S by columns, replicates A and
+exchanges exactly three things per iteration: sum(G_A partials), sum(S S^T partials) for step_A, and the
+three S-block norms.  This test replays that exchange sequence with gloo all-reduces around the oracle's
+NumPy pieces and checks it against the unsharded oracle: it pins the partition (workloads.shard_columns)
+and the list of reduced quantities that the NCCL path relies on."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from oracle import proxmin_oracle as orc
+    from proxmin_b200 import workloads
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def allreduce(x):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    M, N, K = 96, 400, 6
+    Y, A, S = workloads.cfg2(M, N, K, seed=3)
+    lo, hi = workloads.shard_columns(N, world, rank, align=128)
+    Yl, Sl = Y[:, lo:hi].copy(), S[:, lo:hi].copy()
+    A = A.copy()
+    iters = 25
+    for it in range(iters):
+        R = A.dot(Sl) - Yl                                   # local stripe of the residual
+        GA = allreduce(R.dot(Sl.T)).astype(np.float32)       # exchange 1: G_A partials
+        GS = A.T.dot(R)                                      # local
+        gramS = allreduce(Sl.astype(np.float64).dot(Sl.T))   # exchange 2: S S^T partials
+        step_A = np.float32(1 / np.linalg.eigvalsh(gramS).max())
+        step_S = np.float32(1 / orc.lipschitz(A))
+        A_new = orc.prox_plus(A - step_A * GA, step_A)
+        S_new = orc.prox_unity_plus(Sl - step_S * GS, step_S)   # column sums are local to a stripe
+        nS = allreduce(np.array([((S_new - Sl) ** 2).sum(), (S_new ** 2).sum()]))   # exchange 3: S norms
+        A, Sl = A_new, S_new
+    if rank == 0:
+        np.savez(out, A=A, nS=nS)
+    np.save(out + ".S%d.npy" % rank, Sl)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_sharded_pgm_matches_unsharded(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+
+    from oracle import proxmin_oracle as orc
+    from proxmin_b200 import workloads
+
+    world, port = 2, 29611 + os.getpid() % 200
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    got = np.load(out)
+    S = np.concatenate([np.load(out + ".S%d.npy" % r) for r in range(world)], axis=1)
+
+    M, N, K = 96, 400, 6
+    Y, A, S0 = workloads.cfg2(M, N, K, seed=3)
+    orc.nmf(Y, A, S0, prox_A=orc.prox_plus, prox_S=orc.prox_unity_plus, algorithm="pgm", max_iter=25, e_rel=0)
+    assert np.linalg.norm(got["A"] - A) / np.linalg.norm(A) < 2e-5
+    assert np.linalg.norm(S - S0) / np.linalg.norm(S0) < 2e-5
+    assert np.allclose(S.sum(axis=0), 1, atol=1e-5)
