@@ -105,29 +105,59 @@ __global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
 }
 
 // ---- chains with UNITY(axis=0): one thread owns a column (coalesced across threads) -----
+// Rows are processed in batches of RB with all loads issued before the arithmetic, so that a thread
+// keeps RB x (number of input streams) requests in flight: the pass is latency-bound otherwise.
 template <int IN>
-__global__ void __launch_bounds__(kThreads) k_upd_cols(ProxChain ch, UpdIO io) {
+__global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
   if (skip(io)) return;
+  constexpr int RB = 8;
   float nd = 0.f, nn = 0.f, np = 0.f;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < io.cols) {
     const bool alias = (io.Xprev == io.Xout);
     const float* prev_src = alias ? io.Xold_out : io.Xprev;
+    const bool prev_is_in = (io.Xprev == io.Xin);
     int a = 0, b = chain_next_unity(ch, 0);
     // pass 0: transform + first elementwise segment; column sum in row order (NumPy's order for axis=0)
     float sum = 0.f;
-    for (int r = 0; r < io.rows; ++r) {
-      const size_t i = (size_t)r * io.cols + c;
-      const float prev = io.Xprev ? io.Xprev[i] : 0.f;
-      float ps;
-      float v = transform<IN>(io, i, r, c, ps);
-      v = chain_segment(ch, a, b, v, ps);
-      if (io.Xold_out) io.Xold_out[i] = prev;
-      io.Xout[i] = v;
-      sum += v;
-      if (b >= ch.n) {
-        const float d = v - prev;
-        nd += d * d; nn += v * v; np += prev * prev;
+    for (int r0 = 0; r0 < io.rows; r0 += RB) {
+      float xin[RB], g[RB], x0[RB], prev[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int r = r0 + j;
+        if (r < io.rows) {
+          const size_t i = (size_t)r * io.cols + c;
+          xin[j] = io.Xin[i];
+          g[j] = (IN != IN_PLAIN) ? io.G[i] : 0.f;
+          x0[j] = (IN == IN_ADASUB) ? io.X0[i] : 0.f;
+          prev[j] = prev_is_in ? xin[j] : (io.Xprev ? io.Xprev[i] : 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int r = r0 + j;
+        if (r < io.rows) {
+          const size_t i = (size_t)r * io.cols + c;
+          const float s = step_at(io.step, r, c);
+          float ps = s, v;
+          if (IN == IN_PGM) {
+            v = __fsub_rn(xin[j], __fmul_rn(s, g[j]));
+          } else if (IN == IN_ADASUB) {
+            const float gamma = s / io.psimax[0];
+            ps = gamma;
+            v = xin[j] - gamma / s * g[j] * (xin[j] - x0[j]);
+          } else {
+            v = xin[j];
+          }
+          v = chain_segment(ch, a, b, v, ps);
+          if (io.Xold_out) io.Xold_out[i] = prev[j];
+          io.Xout[i] = v;
+          sum += v;
+          if (b >= ch.n) {
+            const float d = v - prev[j];
+            nd += d * d; nn += v * v; np += prev[j] * prev[j];
+          }
+        }
       }
     }
     // one further pass per UNITY op: divide by the column sum, then the next elementwise segment
@@ -136,16 +166,32 @@ __global__ void __launch_bounds__(kThreads) k_upd_cols(ProxChain ch, UpdIO io) {
       b = chain_next_unity(ch, a);
       const float denom = sum;
       sum = 0.f;
-      for (int r = 0; r < io.rows; ++r) {
-        const size_t i = (size_t)r * io.cols + c;
-        float v = io.Xout[i] / denom;                     // operators.py:44
-        v = chain_segment(ch, a, b, v, prox_step<IN>(io, r, c));
-        io.Xout[i] = v;
-        sum += v;
-        if (b >= ch.n) {
-          const float prev = prev_src ? prev_src[i] : 0.f;
-          const float d = v - prev;
-          nd += d * d; nn += v * v; np += prev * prev;
+      const bool last = b >= ch.n;
+      for (int r0 = 0; r0 < io.rows; r0 += RB) {
+        float cur[RB], prev[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int r = r0 + j;
+          if (r < io.rows) {
+            const size_t i = (size_t)r * io.cols + c;
+            cur[j] = io.Xout[i];
+            prev[j] = (last && prev_src) ? prev_src[i] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          const int r = r0 + j;
+          if (r < io.rows) {
+            const size_t i = (size_t)r * io.cols + c;
+            float v = cur[j] / denom;                     // operators.py:44
+            v = chain_segment(ch, a, b, v, prox_step<IN>(io, r, c));
+            io.Xout[i] = v;
+            sum += v;
+            if (last) {
+              const float d = v - prev[j];
+              nd += d * d; nn += v * v; np += prev[j] * prev[j];
+            }
+          }
         }
       }
     }
@@ -220,7 +266,7 @@ int launch_update_t(pmx_ctx* ctx, const ProxChain& chain, const UpdIO& io) {
     if (blocks > cap) blocks = cap;
     k_upd_flat<IN><<<(int)blocks, kThreads, 0, ctx->stream>>>(chain, io);
   } else if (ax == 0) {
-    k_upd_cols<IN><<<pmx_div_up(io.cols, kThreads), kThreads, 0, ctx->stream>>>(chain, io);
+    k_upd_cols<IN><<<pmx_div_up(io.cols, 128), 128, 0, ctx->stream>>>(chain, io);
   } else {
     const int wpb = kThreads / 32;
     long long blocks = pmx_div_up(io.rows, wpb);

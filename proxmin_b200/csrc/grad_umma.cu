@@ -50,13 +50,13 @@ constexpr uint32_t OFF_BAR = OFF_Y + Y_STAGES * PANEL_R;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
 
 enum {  // mbarrier indices
-  B_A_FULL = 0, B_A_EMPTY, B_S_FULL, B_S_EMPTY = B_S_FULL + 2, B_Y_FULL = B_S_EMPTY + 2,
+  B_A_FULL = 0, B_A_EMPTY, B_AOP_FULL, B_S_FULL, B_S_EMPTY = B_S_FULL + 2, B_Y_FULL = B_S_EMPTY + 2,
   B_Y_EMPTY = B_Y_FULL + Y_STAGES, B_ACC_FULL = B_Y_EMPTY + Y_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2,
-  B_R_FULL = B_ACC_EMPTY + 2, B_R_EMPTY, B_GS_FULL, B_GS_EMPTY = B_GS_FULL + 2, B_GA_FULL = B_GS_EMPTY + 2,
-  B_GA_EMPTY, B_COUNT
+  B_RT_FULL = B_ACC_EMPTY + 2, B_RS_FULL = B_RT_FULL + 2, B_RS_EMPTY, B_GS_FULL, B_GS_EMPTY = B_GS_FULL + 2,
+  B_GA_FULL = B_GS_EMPTY + 2, B_GA_EMPTY, B_COUNT
 };
 
-constexpr uint32_t TM_ACC = 0, TM_GS = 256, TM_GA = 384;   // TMEM column offsets
+constexpr uint32_t TM_ACC = 0, TM_GS = 256, TM_GA = 384, TM_AOP = 448;   // TMEM column offsets
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +88,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// TMA prefetch of one box into L2 (no shared memory, no barrier): decouples the HBM latency from the ring depth
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -104,6 +108,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M x 16 bf16 = 128 lanes x 8 columns) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -145,6 +168,7 @@ struct Params {
   float* GS;
   double* loss;
   const int* done;
+  int y_prefetch;         // tiles of Y prefetched into L2 ahead of the shared-memory ring
   int ablate;             // debug/timing only (env PMX_ABLATE): bit0 no MMA1, 1 no MMA2, 2 no MMA3, 3 no Y read, 4 no R store, 5 no G_S flush, 6 no epilogue math
 };
 
@@ -175,7 +199,9 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       uint32_t count = 1;
       if (i >= B_Y_EMPTY && i < B_Y_EMPTY + Y_STAGES) count = NUM_EPI_WARPS / 2;   // one column-chunk group
       if (i == B_ACC_EMPTY || i == B_ACC_EMPTY + 1) count = NUM_EPI_WARPS;
-      if (i == B_R_FULL) count = NUM_EPI_WARPS;
+      if (i == B_RT_FULL || i == B_RT_FULL + 1) count = NUM_EPI_WARPS;
+      if (i == B_RS_FULL) count = NUM_EPI_WARPS;
+      if (i == B_AOP_FULL) count = NUM_EPI_WARPS;
       if (i == B_GS_EMPTY || i == B_GS_EMPTY + 1) count = NUM_EPI_WARPS;
       if (i == B_GA_EMPTY) count = NUM_EPI_WARPS;
       mbar_init(bar(i), count);
@@ -228,10 +254,13 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
+    // Issue order per tile t:  MMA1(t+1) | MMA2(t) | MMA3(t).  tcgen05 MMAs execute in issue order, which
+    // also orders the re-use of the accumulator/R buffers between MMAs; the epilogue's own TMEM accesses
+    // are ordered against them with the mbarriers below.
     if (lane == 0) {
-      constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);  // A tile K-major, S tile MN-major
-      constexpr uint32_t ID_GA = make_idesc(128, 64, 0, 0);    // R K-major, S tile K-major
-      constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);    // R^T (MN-major), A tile MN-major
+      constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);  // A tile from TMEM (K-major), S tile MN-major
+      constexpr uint32_t ID_GA = make_idesc(128, 64, 0, 0);    // R from TMEM (K-major), S tile K-major
+      constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);    // R^T (MN-major, SMEM), A tile MN-major
       uint32_t seg_full = 0;
       const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
 
@@ -239,24 +268,23 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         const uint32_t slot = t & 1;
         mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);
         if (first_in_seg(g)) {
-          mbar_wait(bar(B_A_FULL), seg_full & 1);
+          mbar_wait(bar(B_AOP_FULL), seg_full & 1);   // epilogue warps copied A_hi/A_lo into tensor memory
           ++seg_full;
         }
         mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
         const uint32_t d = tmem + TM_ACC + slot * 128;
-        // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16)
-        const uint32_t a_src[3] = {a_hi, a_hi, a_lo};
+        // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16 = 8 TMEM columns each)
+        const uint32_t a_src[3] = {tmem + TM_AOP, tmem + TM_AOP, tmem + TM_AOP + 32};
         const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
 #pragma unroll
         for (int term = 0; term < 3; ++term)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (p.ablate & 1) continue;
-            const uint64_t ad = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major
             const uint64_t bd = make_desc(s_src[term] + ks * 2048, PANEL_S, 1024);      // MN-major: LBO = next 64 n
-            umma_bf16(d, ad, bd, ID_RES, (term | ks) ? 1u : 0u);
+            umma_bf16_ts(d, a_src[term] + ks * 8, bd, ID_RES, (term | ks) ? 1u : 0u);
           }
         tc_commit(bar(B_ACC_FULL + slot));
       };
@@ -267,28 +295,33 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         const bool has_next = g + 1 < g_end;
         if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a segment
         const uint32_t slot = t & 1;
-        mbar_wait(bar(B_R_FULL), t & 1);
-        mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         const bool first = first_in_seg(g);
-        if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
         const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
-        {  // G_A[m, k] += R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps); accumulates over the segment
+        {  // G_A[m, k] += R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps); R (bf16 hi/lo) sits in the
+           // columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
+          mbar_wait(bar(B_RT_FULL + slot), (t >> 1) & 1);
+          if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
+          tc_fence_after();
           const uint32_t d = tmem + TM_GA;
-          const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
+          const uint32_t racc = tmem + TM_ACC + slot * 128;
+          const uint32_t r_off[3] = {0, 0, 16};
           const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
 #pragma unroll
           for (int term = 0; term < 3; ++term)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               if (p.ablate & 2) continue;
-              const uint64_t ad = make_desc(r_src[term] + (ks >> 2) * PANEL_R + (ks & 3) * 32, 16, 1024);  // K-major
+              const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8 + r_off[term];
               const uint64_t bd = make_desc(s_src[term] + (ks >> 2) * PANEL_S + (ks & 3) * 32, 16, 1024);  // K-major
-              umma_bf16(d, ad, bd, ID_GA, (!first || (term | ks)) ? 1u : 0u);
+              umma_bf16_ts(d, at, bd, ID_GA, (!first || (term | ks)) ? 1u : 0u);
             }
+          tc_commit(bar(B_S_EMPTY + slot));   // S(t) was last used here
         }
         {  // G_S^T[n, k] = R^T A : M = n (128), N = k (64), K = m (128: 8 k-steps); one accumulator per tile
+          mbar_wait(bar(B_RS_FULL), t & 1);
+          mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
           const uint32_t d = tmem + TM_GS + slot * 64;
           const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
           const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
@@ -301,16 +334,15 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
               const uint64_t bd = make_desc(a_src[term] + ks * 2048, 1024, 1024);     // MN-major, one 64-wide atom
               umma_bf16(d, ad, bd, ID_GS, (term | ks) ? 1u : 0u);
             }
+          tc_commit(bar(B_RS_EMPTY));
+          tc_commit(bar(B_GS_FULL + slot));
         }
-        tc_commit(bar(B_R_EMPTY));
-        tc_commit(bar(B_S_EMPTY + slot));
-        tc_commit(bar(B_GS_FULL + slot));
         if (last_in_seg(g)) {
           tc_commit(bar(B_GA_FULL));
           tc_commit(bar(B_A_EMPTY));
           ++seg;
         }
-        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A tile
+        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A operand
       }
     }
   } else if (warp >= 4) {
@@ -346,9 +378,28 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
 
     for (long long g = g_begin; g < g_end; ++g, ++t) {
       const uint32_t slot = t & 1;
+      if (first_in_seg(g)) {
+        // A_hi (group 0) / A_lo (group 1) of this m-block: shared memory -> tensor memory, the A operand of the
+        // residual GEMM.  All residual MMAs of the previous segment have completed (their accumulators were
+        // consumed below), so the operand columns are free.
+        mbar_wait(bar(B_A_FULL), seg & 1);
+        const uint8_t* arow = base_ptr + OFF_A + grp * PANEL_R + row * 128;
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+          w[4 * c] = v4.x; w[4 * c + 1] = v4.y; w[4 * c + 2] = v4.z; w[4 * c + 3] = v4.w;
+        }
+        tmem_st16(lane_addr + TM_AOP + grp * 32, w);
+        tmem_st16(lane_addr + TM_AOP + grp * 32 + 16, w + 16);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_AOP_FULL));
+      }
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
-      mbar_wait(bar(B_R_EMPTY), (t & 1) ^ 1);   // MMAs of the previous tile no longer read R
       tc_fence_after();
+      // ---- phase A: residual -> bf16 (hi, lo), written back over the accumulator columns it came from
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
         const int q = qq * 2 + grp;
@@ -364,41 +415,57 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
                                  : *reinterpret_cast<const float4*>(yrow + ((c ^ (row & 7)) << 4));
         tmem_ld_wait();
         const float* yf = reinterpret_cast<const float*>(yv);
-        uint32_t hi[16], lo[16];
+        uint32_t hl[32];   // [0,16) = hi pairs, [16,32) = lo pairs
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          if (p.ablate & 64) { hi[j >> 1] = acc[j]; lo[j >> 1] = acc[j + 1]; continue; }
           const float r0 = __uint_as_float(acc[j]) - yf[j];          // nmf.py:40  (A S - Y)
           const float r1 = __uint_as_float(acc[j + 1]) - yf[j + 1];
-          loss_part = fmaf(r0, r0, loss_part);
-          loss_part = fmaf(r1, r1, loss_part);
+          if (p.loss) {
+            loss_part = fmaf(r0, r0, loss_part);
+            loss_part = fmaf(r1, r1, loss_part);
+          }
           const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
           const float2 hf = __bfloat1622float2(h);
           const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - hf.x, r1 - hf.y);
-          hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+          hl[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          hl[16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        // R_hi / R_lo: panel q/2, chunks (q&1)*4 .. +3 of this row
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));
+        tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32, hl);
+        tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32 + 16, hl + 16);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_RT_FULL + slot));       // MMA2(t) may start
+      // ---- phase B: copy R to shared memory (the MN-major operand of the G_S GEMM) once MMA3(t-1) released it
+      mbar_wait(bar(B_RS_EMPTY), (t & 1) ^ 1);
+#pragma unroll 1
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = qq * 2 + grp;
+        uint32_t hl[32];
+        tmem_ld32(lane_addr + TM_ACC + slot * 128 + q * 32, hl);
+        tmem_ld_wait();
         uint8_t* rh = base_ptr + OFF_R_HI + (q >> 1) * PANEL_R + row * 128;
         uint8_t* rl = base_ptr + OFF_R_LO + (q >> 1) * PANEL_R + row * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (p.ablate & 16) continue;
           const int chunk = ((q & 1) * 4 + c) ^ (row & 7);
-          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-          *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hl[4 * c], hl[4 * c + 1], hl[4 * c + 2], hl[4 * c + 3]);
+          *reinterpret_cast<uint4*>(rl + (chunk << 4)) =
+              make_uint4(hl[16 + 4 * c], hl[16 + 4 * c + 1], hl[16 + 4 * c + 2], hl[16 + 4 * c + 3]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));
       }
       tc_fence_before();
       fence_async_smem();   // generic-proxy writes of R -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(B_ACC_EMPTY + slot));
-        mbar_arrive(bar(B_R_FULL));
+        mbar_arrive(bar(B_RS_FULL));             // MMA3(t) may start
+        mbar_arrive(bar(B_ACC_EMPTY + slot));    // our reads of this accumulator/R buffer are done
       }
-      // deferred flush of the previous tile's G_S^T (its MMAs finished while we built this R)
+      // deferred flush of the previous tile's G_S^T (its MMAs finished before MMA3(t-1) released R)
       if (pending_g >= 0) flush_gs(pending_g, pending_t);
       pending_g = g;
       pending_t = t;
@@ -546,6 +613,8 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   {
     const char* ab = getenv("PMX_ABLATE");
     p.ablate = ab ? atoi(ab) : 0;
+    const char* pf = getenv("PMX_Y_PREFETCH");
+    p.y_prefetch = pf ? atoi(pf) : 4;
   }
   int grid = (int)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;

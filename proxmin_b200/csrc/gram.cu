@@ -90,9 +90,13 @@ __global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int r
 }
 
 // One CTA (1024 threads).  gram: C x C fp64 (symmetric PSD).  which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].
-__global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ gram, int C, pmx_ctl* ctl, int which,
-                                                     int squarings) {
+__global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ gram0, int which0,
+                                                     const double* __restrict__ gram1, int which1, int C,
+                                                     pmx_ctl* ctl, int squarings) {
   if (ctl->done) return;
+  // one CTA per Gram matrix (gridDim.x = 1 or 2)
+  const double* __restrict__ gram = blockIdx.x == 0 ? gram0 : gram1;
+  const int which = blockIdx.x == 0 ? which0 : which1;
   extern __shared__ __align__(16) float smem[];
   const int C4 = (C + 3) & ~3;
   const int ldt = C4 + 4;
@@ -183,12 +187,16 @@ __global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ 
       s_scalar = t;
     }
     __syncthreads();
+    // tr(B^2) with tr(B) = 1 equals sum_i w_i^2 of the normalised spectrum: it reaches 1 when the power is
+    // rank one to fp32 resolution -- no further squaring can change the selected column
+    const bool rank_one = (1.0 - s_scalar) < 2e-6;
     const float inv = (float)(1.0 / s_scalar);
     for (int idx = tid; idx < C4 * ldt; idx += blockDim.x) nxt[idx] *= inv;
     __syncthreads();
     float* tmp = cur;
     cur = nxt;
     nxt = tmp;
+    if (rank_one) break;   // block-uniform (s_scalar is shared)
   }
   // v = column of the (near rank-one) power with the largest diagonal entry
   if (tid == 0) {
@@ -264,7 +272,16 @@ int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int col
   return pmx_check_launch(ctx, "k_gram");
 }
 
+int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
+                       int C, pmx_ctl* ctl);
+
 int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which) {
+  return launch_lambda_max2(ctx, st, gram, which, nullptr, 0, C, ctl);
+}
+
+// one launch for one or two Gram matrices (two CTAs run concurrently)
+int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
+                       int C, pmx_ctl* ctl) {
   if (C > kMaxK) {
     pmx_set_error("Gram dimension K=%d exceeds the supported maximum %d", C, kMaxK);
     return PMX_ERR_UNSUPPORTED;
@@ -280,7 +297,7 @@ int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, 
     }
     attr_set = true;
   }
-  k_lambda_max<<<1, 1024, smem, st>>>(gram, C, ctl, which, 16);
+  k_lambda_max<<<gram1 ? 2 : 1, 1024, smem, st>>>(gram0, which0, gram1, which1, C, ctl, 20);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_lambda_max");
 }

@@ -10,6 +10,8 @@ int launch_split_bf16(pmx_ctx* ctx, const float* X, int rows, int cols, void* hi
 int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int cols, bool tall, double* gram,
                 const int* done);
 int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which);
+int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
+                       int C, pmx_ctl* ctl);
 int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done);
 

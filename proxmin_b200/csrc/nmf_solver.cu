@@ -104,12 +104,14 @@ int nmf_steps(pmx_nmf* h, const float* A, const float* S, bool need_A, bool need
   if (need_A) {  // step for A needs the Gram of S (sum over this rank's columns, then over ranks)
     PMX_CHECK(launch_gram(ctx, ctx->aux, S, h->K, h->N, false, h->gramS, &h->ctl->done));
     if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->aux));
+  }
+  if (need_S) PMX_CHECK(launch_gram(ctx, ctx->aux, A, h->M, h->K, true, h->gramA, &h->ctl->done));
+  if (need_A && need_S)
+    PMX_CHECK(launch_lambda_max2(ctx, ctx->aux, h->gramS, 0, h->gramA, 1, h->K, h->ctl));
+  else if (need_A)
     PMX_CHECK(launch_lambda_max(ctx, ctx->aux, h->gramS, h->K, h->ctl, 0));
-  }
-  if (need_S) {
-    PMX_CHECK(launch_gram(ctx, ctx->aux, A, h->M, h->K, true, h->gramA, &h->ctl->done));
+  else if (need_S)
     PMX_CHECK(launch_lambda_max(ctx, ctx->aux, h->gramA, h->K, h->ctl, 1));
-  }
   PMX_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
   return PMX_OK;
 }

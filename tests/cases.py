@@ -244,11 +244,15 @@ def nmf_adaprox_schemes(api):
 
 @case
 def nmf_bsdmm(api):
-    """config 5 recipe scaled down: bsdmm, direct prox_id, constraints via proxs_g."""
+    """config 5 recipe scaled down: bsdmm, direct prox_id, constraints via proxs_g.
+
+    Horizon: 6 outer iterations.  The reference's own bsdmm trajectory on this problem is chaotic: scaling Y
+    by (1 + 1e-6) changes the reference's A by 2e-6 after 6, 7e-5 after 12 and 18 % after 20 iterations
+    (measured with the oracle), so longer horizons cannot separate implementation error from sensitivity."""
     Y, A, S = workloads.cfg5(96, 256, 8, seed=9)
     proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus, partial(api.prox_soft, thresh=0.01)]]
     conv = api.nmf.nmf(Y, A, S, algorithm=api.bsdmm, prox_A=api.prox_id, prox_S=api.prox_id,
-                       proxs_g=proxs_g, max_iter=20, e_rel=1e-6)
+                       proxs_g=proxs_g, max_iter=6, e_rel=1e-6)
     return _pack(api, A, S, {"converged": np.array([bool(c) for c in conv])})
 
 
