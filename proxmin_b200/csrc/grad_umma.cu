@@ -22,10 +22,9 @@
 //   Y ring     4 x [128 m-rows][32 fp32]       64 KB   4 sub-tiles/tile  (TMA)
 // TMEM (512 columns): residual accumulator 2 x 128, G_S^T accumulator 2 x 64, G_A accumulator 64.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..11 = epilogue (TMEM -> registers -> residual -> SMEM, gradient flushes); two warps share
-// each TMEM lane quarter and split the column chunks so that every SM sub-partition has two
-// epilogue warps to hide the TMEM / shared-memory latencies.
+// Warp roles (512 threads): warp 0 = TMA producer, warps 1 and 3 = MMA issuers (residual + G_A / G_S),
+// warp 2 = TMEM allocator, warps 4..11 = residual warps (TMEM accumulator -> R in TMEM and SMEM; two warps
+// share each TMEM lane quarter and split the column chunks), warps 12..15 = gradient flush warps.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -50,13 +49,15 @@ constexpr uint32_t OFF_BAR = OFF_Y + Y_STAGES * PANEL_R;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
 
 enum {  // mbarrier indices
-  B_A_FULL = 0, B_A_EMPTY, B_AOP_FULL, B_S_FULL, B_S_EMPTY = B_S_FULL + 2, B_Y_FULL = B_S_EMPTY + 2,
+  B_A_FULL = 0, B_A_EMPTY, B_S_FULL, B_S_EMPTY = B_S_FULL + 2, B_Y_FULL = B_S_EMPTY + 2,
   B_Y_EMPTY = B_Y_FULL + Y_STAGES, B_ACC_FULL = B_Y_EMPTY + Y_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2,
   B_RT_FULL = B_ACC_EMPTY + 2, B_RS_FULL = B_RT_FULL + 2, B_RS_EMPTY, B_GS_FULL, B_GS_EMPTY = B_GS_FULL + 2,
   B_GA_FULL = B_GS_EMPTY + 2, B_GA_EMPTY, B_COUNT
 };
 
-constexpr uint32_t TM_ACC = 0, TM_GS = 256, TM_GA = 384, TM_AOP = 448;   // TMEM column offsets
+// TMEM column map (512): residual accumulator / R operand 2 x 128, G_S^T 2 x 64 (double-buffered so that the
+// red.add flush of tile t overlaps the MMAs of tile t+1), G_A [hh|hl] 128
+constexpr uint32_t TM_ACC = 0, TM_GS = 256, TM_GA = 384;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +82,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// single non-blocking probe of a barrier phase (test_wait returns immediately; try_wait may suspend the thread
+// for a system-dependent time when the phase is not complete)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(
@@ -118,6 +132,35 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The issuer warps run warp-uniform code and elect one lane inside the asm statement: descriptors and tensor
+// memory addresses then stay in uniform registers instead of being broadcast lane by lane before every MMA.
+__device__ __forceinline__ void umma_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -142,6 +185,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// In-register 4x4 transpose across the 4 lanes of a quad: before, lane r holds row r = (v0..v3);
+// after, lane r holds column r.  Two xor-butterfly rounds (2x2 blocks across lane^1, then lane^2).
+__device__ __forceinline__ void quad_transpose(float& v0, float& v1, float& v2, float& v3, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  float x, y;
+  x = b0 ? v0 : v1; y = __shfl_xor_sync(0xffffffffu, x, 1); if (b0) v0 = y; else v1 = y;
+  x = b0 ? v2 : v3; y = __shfl_xor_sync(0xffffffffu, x, 1); if (b0) v2 = y; else v3 = y;
+  x = b1 ? v0 : v2; y = __shfl_xor_sync(0xffffffffu, x, 2); if (b1) v0 = y; else v2 = y;
+  x = b1 ? v1 : v3; y = __shfl_xor_sync(0xffffffffu, x, 2); if (b1) v1 = y; else v3 = y;
 }
 
 // UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor layout, version 1)
@@ -169,11 +223,22 @@ struct Params {
   double* loss;
   const int* done;
   int y_prefetch;         // tiles of Y prefetched into L2 ahead of the shared-memory ring
+  long long* trace;       // debug: clock64 timeline of CTA 0 (env PMX_TRACE), [role][tile][event]
   int ablate;             // debug/timing only (env PMX_ABLATE): bit0 no MMA1, 1 no MMA2, 2 no MMA3, 3 no Y read, 4 no R store, 5 no G_S flush, 6 no epilogue math
 };
 
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
+// timeline tracing (debug only): role r, local tile index t, event e
+#define TRACE_TILES 24
+#define TRACE_EVENTS 8
+#define TR(r, t, e)                                                                                   \
+  do {                                                                                                \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (t) < TRACE_TILES)                                 \
+      p.trace[((r) * TRACE_TILES + (t)) * TRACE_EVENTS + (e)] = clock64();                            \
+  } while (0)
+
+constexpr int NUM_EPI_WARPS = 8;     // residual warps: TMEM accumulator -> R (TMEM + SMEM)
+constexpr int NUM_FLUSH_WARPS = 4;   // gradient flush warps: TMEM accumulators -> red.add to global memory
+constexpr int NUM_THREADS = 128 + 32 * (NUM_EPI_WARPS + NUM_FLUSH_WARPS);
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAhi,
@@ -197,13 +262,13 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       uint32_t count = 1;
+      if (i == B_A_EMPTY) count = 2;                                              // both issuer warps release A
       if (i >= B_Y_EMPTY && i < B_Y_EMPTY + Y_STAGES) count = NUM_EPI_WARPS / 2;   // one column-chunk group
       if (i == B_ACC_EMPTY || i == B_ACC_EMPTY + 1) count = NUM_EPI_WARPS;
       if (i == B_RT_FULL || i == B_RT_FULL + 1) count = NUM_EPI_WARPS;
       if (i == B_RS_FULL) count = NUM_EPI_WARPS;
-      if (i == B_AOP_FULL) count = NUM_EPI_WARPS;
-      if (i == B_GS_EMPTY || i == B_GS_EMPTY + 1) count = NUM_EPI_WARPS;
-      if (i == B_GA_EMPTY) count = NUM_EPI_WARPS;
+      if (i == B_GS_EMPTY || i == B_GS_EMPTY + 1) count = NUM_FLUSH_WARPS;
+      if (i == B_GA_EMPTY) count = NUM_FLUSH_WARPS;
       mbar_init(bar(i), count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -215,10 +280,13 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   auto first_in_seg = [&](long long g) { return g == g_begin || (g % p.NS) == 0; };
   auto last_in_seg = [&](long long g) { return g == g_end - 1 || (g % p.NS) == p.NS - 1; };
+  // S slot layout: n-panel pn (64 columns) = [S_hi 64 k-rows | S_lo 64 k-rows] -> 16 KB per panel, so that
+  // [S_hi; S_lo] is one 128-row K-major operand (the "stacked" N = 128 operand of the G_A GEMM)
+  constexpr uint32_t S_SLOT = 4 * PANEL_S, S_PANEL = 2 * PANEL_S;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -228,21 +296,20 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         const int mb = (int)(g / p.NS), stripe = (int)(g % p.NS);
         const int m0 = mb * TILE_M, n0 = stripe * TILE_N;
         const uint32_t slot = t & 1;
-        // S stripe tile (hi, lo): 4 boxes of 64 k-rows x 64 columns
         mbar_wait(bar(B_S_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(bar(B_S_FULL + slot), 4 * PANEL_S);
-        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
-        tma_load_2d(s_hi, &tmShi, n0, 0, bar(B_S_FULL + slot));
-        tma_load_2d(s_hi + PANEL_S, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot));
-        tma_load_2d(s_lo, &tmSlo, n0, 0, bar(B_S_FULL + slot));
-        tma_load_2d(s_lo + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot));
-        // Y sub-tiles
+        const uint32_t sb = base + OFF_S + slot * S_SLOT;
+        tma_load_2d(sb, &tmShi, n0, 0, bar(B_S_FULL + slot));
+        tma_load_2d(sb + PANEL_S, &tmSlo, n0, 0, bar(B_S_FULL + slot));
+        tma_load_2d(sb + S_PANEL, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot));
+        tma_load_2d(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot));
+        TR(0, t, 0);
         for (int q = 0; q < 4; ++q) {
           mbar_wait(bar(B_Y_EMPTY + q), (t & 1) ^ 1);
           mbar_expect_tx(bar(B_Y_FULL + q), PANEL_R);
           tma_load_2d(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q));
+          TR(0, t, 1 + q);
         }
-        // A tile of the m-block (after the prefetch above so that a segment switch does not stall it)
         if (first_in_seg(g)) {
           mbar_wait(bar(B_A_EMPTY), (seg & 1) ^ 1);
           mbar_expect_tx(bar(B_A_FULL), 2 * PANEL_R);
@@ -253,166 +320,147 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    // Issue order per tile t:  MMA1(t+1) | MMA2(t) | MMA3(t).  tcgen05 MMAs execute in issue order, which
-    // also orders the re-use of the accumulator/R buffers between MMAs; the epilogue's own TMEM accesses
-    // are ordered against them with the mbarriers below.
-    if (lane == 0) {
-      constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);  // A tile from TMEM (K-major), S tile MN-major
-      constexpr uint32_t ID_GA = make_idesc(128, 64, 0, 0);    // R from TMEM (K-major), S tile K-major
-      constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);    // R^T (MN-major, SMEM), A tile MN-major
-      uint32_t seg_full = 0;
-      const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
+    // ============================== MMA issuer 1: residual GEMM and G_A GEMM ==============================
+    // Issue order per tile t:  MMA1(t+1) | MMA2(t).  All 32 lanes run this loop; one elected lane issues.
+    constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);   // A tile K-major (SMEM), S tile MN-major
+    constexpr uint32_t ID_GA2 = make_idesc(128, 128, 0, 0);   // R_hi from TMEM x [S_hi;S_lo] K-major, N = 128
+    constexpr uint32_t ID_GA1 = make_idesc(128, 64, 0, 0);    // R_lo from TMEM x S_hi, N = 64
+    uint32_t seg_full = 0;
+    const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
 
-      auto issue_residual = [&](long long g, uint32_t t) {
-        const uint32_t slot = t & 1;
-        mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);
-        if (first_in_seg(g)) {
-          mbar_wait(bar(B_AOP_FULL), seg_full & 1);   // epilogue warps copied A_hi/A_lo into tensor memory
-          ++seg_full;
-        }
-        mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
-        const uint32_t d = tmem + TM_ACC + slot * 128;
-        // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16 = 8 TMEM columns each)
-        const uint32_t a_src[3] = {tmem + TM_AOP, tmem + TM_AOP, tmem + TM_AOP + 32};
-        const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
-#pragma unroll
-        for (int term = 0; term < 3; ++term)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (p.ablate & 1) continue;
-            const uint64_t bd = make_desc(s_src[term] + ks * 2048, PANEL_S, 1024);      // MN-major: LBO = next 64 n
-            umma_bf16_ts(d, a_src[term] + ks * 8, bd, ID_RES, (term | ks) ? 1u : 0u);
-          }
-        tc_commit(bar(B_ACC_FULL + slot));
-      };
-
-      uint32_t t = 0, seg = 0;
-      if (g_begin < g_end) issue_residual(g_begin, 0);
-      for (long long g = g_begin; g < g_end; ++g, ++t) {
-        const bool has_next = g + 1 < g_end;
-        if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a segment
-        const uint32_t slot = t & 1;
-        const bool first = first_in_seg(g);
-        const uint32_t s_hi = base + OFF_S + slot * 4 * PANEL_S, s_lo = s_hi + 2 * PANEL_S;
-        {  // G_A[m, k] += R S^T : M = m (128), N = k (64), K = n (128: 8 k-steps); R (bf16 hi/lo) sits in the
-           // columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
-          mbar_wait(bar(B_RT_FULL + slot), (t >> 1) & 1);
-          if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d = tmem + TM_GA;
-          const uint32_t racc = tmem + TM_ACC + slot * 128;
-          const uint32_t r_off[3] = {0, 0, 16};
-          const uint32_t s_src[3] = {s_hi, s_lo, s_hi};
-#pragma unroll
-          for (int term = 0; term < 3; ++term)
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              if (p.ablate & 2) continue;
-              const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8 + r_off[term];
-              const uint64_t bd = make_desc(s_src[term] + (ks >> 2) * PANEL_S + (ks & 3) * 32, 16, 1024);  // K-major
-              umma_bf16_ts(d, at, bd, ID_GA, (!first || (term | ks)) ? 1u : 0u);
-            }
-          tc_commit(bar(B_S_EMPTY + slot));   // S(t) was last used here
-        }
-        {  // G_S^T[n, k] = R^T A : M = n (128), N = k (64), K = m (128: 8 k-steps); one accumulator per tile
-          mbar_wait(bar(B_RS_FULL), t & 1);
-          mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
-          const uint32_t d = tmem + TM_GS + slot * 64;
-          const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
-          const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
-#pragma unroll
-          for (int term = 0; term < 3; ++term)
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              if (p.ablate & 4) continue;
-              const uint64_t ad = make_desc(r_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major: LBO = next 64 n
-              const uint64_t bd = make_desc(a_src[term] + ks * 2048, 1024, 1024);     // MN-major, one 64-wide atom
-              umma_bf16(d, ad, bd, ID_GS, (term | ks) ? 1u : 0u);
-            }
-          tc_commit(bar(B_RS_EMPTY));
-          tc_commit(bar(B_GS_FULL + slot));
-        }
-        if (last_in_seg(g)) {
-          tc_commit(bar(B_GA_FULL));
-          tc_commit(bar(B_A_EMPTY));
-          ++seg;
-        }
-        if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A operand
+    auto issue_residual = [&](long long g, uint32_t t) {
+      const uint32_t slot = t & 1;
+      mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);
+      if (first_in_seg(g)) {
+        mbar_wait(bar(B_A_FULL), seg_full & 1);
+        ++seg_full;
       }
-    }
-  } else if (warp >= 4) {
-    // ============================== epilogue (8 warps) ==============================
-    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;         // column-chunk group: chunks q with (q & 1) == grp
-    const int row = q4 * 32 + lane;          // row of the tile (m for acc / G_A, n for G_S^T)
-    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
-    float loss_part = 0.f;
-    uint32_t t = 0, seg = 0;
-    long long pending_g = -1;   // tile whose G_S^T accumulator still has to be flushed
-    uint32_t pending_t = 0;
-
-    // G_S^T[n, k] -> G_S[k, n]: for a fixed k the 32 lanes of a warp hit 32 consecutive floats (one line)
-    auto flush_gs = [&](long long g, uint32_t tt) {
-      const uint32_t slot = tt & 1;
-      const int n = (int)(g % p.NS) * TILE_N + row;
-      mbar_wait(bar(B_GS_FULL + slot), (tt >> 1) & 1);
+      mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(lane_addr + TM_GS + slot * 64 + grp * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
-      if (n < p.N && !(p.ablate & 32)) {
-        float* dst = p.GS + (size_t)(grp * 32) * p.N + n;
+      TR(1, t, 0);
+      const uint32_t sb = base + OFF_S + slot * S_SLOT;
+      const uint32_t d = tmem + TM_ACC + slot * 128;
+      // acc = A_hi S_hi + A_hi S_lo + A_lo S_hi      (K = 64: 4 k-steps of 16)
+      const uint32_t a_src[3] = {a_hi, a_hi, a_lo};
+      const uint32_t s_src[3] = {sb, sb + PANEL_S, sb};
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (grp * 32 + k < p.K) atomicAdd(dst + (size_t)k * p.N, __uint_as_float(v[k]));
-      }
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (p.ablate & 1) continue;
+          const uint64_t ad = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major
+          const uint64_t bd = make_desc(s_src[term] + ks * 2048, S_PANEL, 1024);      // MN-major: LBO = next 64 n
+          umma_ss_e(d, ad, bd, ID_RES, (term | ks) ? 1u : 0u);
+        }
+      tc_commit_e(bar(B_ACC_FULL + slot));
+      TR(1, t, 1);
     };
 
+    // Blocking, in-order issue (a polling issuer that picks whichever stream is ready was measured slower: the
+    // spinning warp steals issue slots from the residual warps of its SM sub-partition).
+    uint32_t t = 0, seg = 0;
+    if (g_begin < g_end) issue_residual(g_begin, 0);
+    for (long long g = g_begin; g < g_end; ++g, ++t) {
+      const bool has_next = g + 1 < g_end;
+      if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a segment
+      const uint32_t slot = t & 1;
+      const bool first = first_in_seg(g);
+      // G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (K = n: 8 k-steps).  R (bf16 hi/lo)
+      // sits in the columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
+      mbar_wait(bar(B_RT_FULL + slot), (t >> 1) & 1);
+      if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
+      tc_fence_after();
+      TR(1, t, 2);
+      const uint32_t sb = base + OFF_S + slot * S_SLOT;
+      const uint32_t d = tmem + TM_GA;
+      const uint32_t racc = tmem + TM_ACC + slot * 128;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        if (p.ablate & 2) continue;
+        const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8;
+        const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);   // K-major, 128 rows
+        umma_ts_e(d, at, bd, ID_GA2, (!first || ks) ? 1u : 0u);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        if (p.ablate & 2) continue;
+        const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8 + 16;
+        const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);   // K-major, rows 0..63
+        umma_ts_e(d, at, bd, ID_GA1, 1u);
+      }
+      tc_commit_e(bar(B_S_EMPTY + slot));   // S(t) was last used here
+      TR(1, t, 3);
+      if (last_in_seg(g)) {
+        tc_commit_e(bar(B_GA_FULL));
+        tc_commit_e(bar(B_A_EMPTY));        // residual GEMMs of this segment are done with the A tile
+        ++seg;
+      }
+      if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A tile
+    }
+  } else if (warp == 3) {
+    // ============================== MMA issuer 2: G_S GEMM ==============================
+    // G_S^T[n, k] = R_hi^T A_hi + R_hi^T A_lo + R_lo^T A_hi   (M = n, N = k = 64, K = m: 8 k-steps), R^T from SMEM
+    constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);
+    const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
+    const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
+    uint32_t t = 0, seg_full = 0;
     for (long long g = g_begin; g < g_end; ++g, ++t) {
       const uint32_t slot = t & 1;
       if (first_in_seg(g)) {
-        // A_hi (group 0) / A_lo (group 1) of this m-block: shared memory -> tensor memory, the A operand of the
-        // residual GEMM.  All residual MMAs of the previous segment have completed (their accumulators were
-        // consumed below), so the operand columns are free.
-        mbar_wait(bar(B_A_FULL), seg & 1);
-        const uint8_t* arow = base_ptr + OFF_A + grp * PANEL_R + row * 128;
-        uint32_t w[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 v4 = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-          w[4 * c] = v4.x; w[4 * c + 1] = v4.y; w[4 * c + 2] = v4.z; w[4 * c + 3] = v4.w;
-        }
-        tmem_st16(lane_addr + TM_AOP + grp * 32, w);
-        tmem_st16(lane_addr + TM_AOP + grp * 32 + 16, w + 16);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_AOP_FULL));
+        mbar_wait(bar(B_A_FULL), seg_full & 1);
+        ++seg_full;
       }
+      mbar_wait(bar(B_RS_FULL), t & 1);
+      TR(2, t, 2);
+      mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      TR(2, t, 0);
+      const uint32_t d = tmem + TM_GS + slot * 64;
+      const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
+      const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (p.ablate & 4) continue;
+          const uint64_t ad = make_desc(r_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major: LBO = next 64 n
+          const uint64_t bd = make_desc(a_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major, one 64-wide atom
+          umma_ss_e(d, ad, bd, ID_GS, (term | ks) ? 1u : 0u);
+        }
+      tc_commit_e(bar(B_RS_EMPTY));
+      tc_commit_e(bar(B_GS_FULL + slot));
+      TR(2, t, 1);
+      if (last_in_seg(g)) tc_commit_e(bar(B_A_EMPTY));
+    }
+  } else if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) {
+    // ============================== residual warps (8) ==============================
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;         // column-chunk group: chunks q with (q & 1) == grp
+    const int row = q4 * 32 + lane;          // row m of the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    float loss_part = 0.f;
+    uint32_t t = 0;
+    for (long long g = g_begin; g < g_end; ++g, ++t) {
+      const uint32_t slot = t & 1;
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
       tc_fence_after();
+      if (warp == 4) TR(3, t, 0);
       // ---- phase A: residual -> bf16 (hi, lo), written back over the accumulator columns it came from
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
         const int q = qq * 2 + grp;
         mbar_wait(bar(B_Y_FULL + q), t & 1);
+        if (warp == 4) TR(3, t, 1 + qq);
         uint32_t acc[32];
         tmem_ld32(lane_addr + TM_ACC + slot * 128 + q * 32, acc);
-        // this row of the Y sub-tile: 8 x 16-byte chunks, 128B-swizzled by TMA
         const uint8_t* yrow = base_ptr + OFF_Y + q * PANEL_R + row * 128;
         float4 yv[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           yv[c] = (p.ablate & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                  : *reinterpret_cast<const float4*>(yrow + ((c ^ (row & 7)) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));   // the Y values are in registers: refill the slot now
         tmem_ld_wait();
         const float* yf = reinterpret_cast<const float*>(yv);
         uint32_t hl[32];   // [0,16) = hi pairs, [16,32) = lo pairs
@@ -430,8 +478,6 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
           hl[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           hl[16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));
         tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32, hl);
         tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32 + 16, hl + 16);
       }
@@ -439,8 +485,10 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_RT_FULL + slot));       // MMA2(t) may start
+      if (warp == 4) TR(3, t, 3);
       // ---- phase B: copy R to shared memory (the MN-major operand of the G_S GEMM) once MMA3(t-1) released it
       mbar_wait(bar(B_RS_EMPTY), (t & 1) ^ 1);
+      if (warp == 4) TR(3, t, 4);
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
         const int q = qq * 2 + grp;
@@ -465,44 +513,105 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         mbar_arrive(bar(B_RS_FULL));             // MMA3(t) may start
         mbar_arrive(bar(B_ACC_EMPTY + slot));    // our reads of this accumulator/R buffer are done
       }
-      // deferred flush of the previous tile's G_S^T (its MMAs finished before MMA3(t-1) released R)
-      if (pending_g >= 0) flush_gs(pending_g, pending_t);
-      pending_g = g;
-      pending_t = t;
-      if (last_in_seg(g)) {
-        flush_gs(g, t);  // waits for this tile's MMAs
-        pending_g = -1;
-        // G_A[m, k] of the whole segment: once per m-block row and CTA
-        mbar_wait(bar(B_GA_FULL), seg & 1);
-        tc_fence_after();
-        const int m = (int)(g / p.NS) * TILE_M + row;
-        uint32_t v[32];
-        tmem_ld32(lane_addr + TM_GA + grp * 32, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
-        if (m < p.M) {
-          float* dst = p.GA + (size_t)m * p.K + grp * 32;
-          if ((p.K & 3) == 0) {
-#pragma unroll
-            for (int k = 0; k < 32; k += 4)
-              if (grp * 32 + k < p.K)
-                red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
-                           __uint_as_float(v[k + 3]));
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (grp * 32 + k < p.K) atomicAdd(dst + k, __uint_as_float(v[k]));
-          }
-        }
-        ++seg;
-      }
+      if (warp == 4) TR(3, t, 5);
     }
     if (p.loss) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
       if (lane == 0) atomicAdd(p.loss, 0.5 * (double)loss_part);
+    }
+  } else if (warp >= 4 + NUM_EPI_WARPS) {
+    // ============================== gradient flush warps (4) ==============================
+    // The red.add traffic (32 KB per tile into the L2-resident G_S) back-pressures the issuing warp; keeping it
+    // on dedicated warps takes it off the residual warps' critical loop.
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;          // n for G_S^T, m for G_A
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    uint32_t t = 0, seg = 0;
+    for (long long g = g_begin; g < g_end; ++g, ++t) {
+      {  // G_S^T[n, k] = hh + hl halves -> G_S[k, n]: for a fixed k the 32 lanes hit one 128-byte line
+        const int n = (int)(g % p.NS) * TILE_N + row;
+        const uint32_t slot = t & 1;
+        mbar_wait(bar(B_GS_FULL + slot), (t >> 1) & 1);
+        tc_fence_after();
+        if (warp == 12) TR(4, t, 0);
+        uint32_t v[32], w[32];
+        tmem_ld32(lane_addr + TM_GS + slot * 64, v);
+        tmem_ld32(lane_addr + TM_GS + slot * 64 + 32, w);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
+        if (warp == 12) TR(4, t, 1);
+        if (!(p.ablate & 32)) {
+          if ((p.N & 3) == 0) {
+            // 4x4 quad transposes: lane 4j+r ends up with G_S[k = 4i+r][n = 4j .. 4j+3] -> one 16-byte red per
+            // 4 values (16 instead of 64 reductions per thread; a warp-level red covers 4 full 128-byte lines)
+            const int nq = (int)(g % p.NS) * TILE_N + q4 * 32 + (lane & ~3);
+            const int r = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a0 = __uint_as_float(v[4 * i]), a1 = __uint_as_float(v[4 * i + 1]);
+              float a2 = __uint_as_float(v[4 * i + 2]), a3 = __uint_as_float(v[4 * i + 3]);
+              quad_transpose(a0, a1, a2, a3, lane);
+              const int k = 4 * i + r;
+              if (k < p.K && nq < p.N) red_add_v4(p.GS + (size_t)k * p.N + nq, a0, a1, a2, a3);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a0 = __uint_as_float(w[4 * i]), a1 = __uint_as_float(w[4 * i + 1]);
+              float a2 = __uint_as_float(w[4 * i + 2]), a3 = __uint_as_float(w[4 * i + 3]);
+              quad_transpose(a0, a1, a2, a3, lane);
+              const int k = 32 + 4 * i + r;
+              if (k < p.K && nq < p.N) red_add_v4(p.GS + (size_t)k * p.N + nq, a0, a1, a2, a3);
+            }
+          } else if (n < p.N) {
+            float* dst = p.GS + n;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < p.K) atomicAdd(dst + (size_t)k * p.N, __uint_as_float(v[k]));
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (32 + k < p.K) atomicAdd(dst + (size_t)(32 + k) * p.N, __uint_as_float(w[k]));
+          }
+        }
+        if (warp == 12) TR(4, t, 2);
+      }
+      if (last_in_seg(g)) {
+        // G_A[m, k] = hh + hl halves of the whole segment: once per m-block row and CTA
+        mbar_wait(bar(B_GA_FULL), seg & 1);
+        tc_fence_after();
+        const int m = (int)(g / p.NS) * TILE_M + row;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32], w[32];
+          tmem_ld32(lane_addr + TM_GA + half * 32, v);
+          tmem_ld32(lane_addr + TM_GA + 64 + half * 32, w);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
+          }
+          if (m < p.M) {
+            float* dst = p.GA + (size_t)m * p.K + half * 32;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(w[k]));
+            if ((p.K & 3) == 0) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4)
+                if (half * 32 + k < p.K)
+                  red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                             __uint_as_float(v[k + 3]));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (half * 32 + k < p.K) atomicAdd(dst + k, __uint_as_float(v[k]));
+            }
+          }
+        }
+        ++seg;
+      }
     }
   }
 
@@ -613,8 +722,15 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   {
     const char* ab = getenv("PMX_ABLATE");
     p.ablate = ab ? atoi(ab) : 0;
+    static long long* d_trace = nullptr;
+    p.trace = nullptr;
+    if (getenv("PMX_TRACE")) {
+      if (!d_trace) cudaMalloc((void**)&d_trace, sizeof(long long) * 5 * TRACE_TILES * TRACE_EVENTS);
+      cudaMemsetAsync(d_trace, 0, sizeof(long long) * 5 * TRACE_TILES * TRACE_EVENTS, ctx->stream);
+      p.trace = d_trace;
+    }
     const char* pf = getenv("PMX_Y_PREFETCH");
-    p.y_prefetch = pf ? atoi(pf) : 4;
+    p.y_prefetch = pf ? atoi(pf) : 0;
   }
   int grid = (int)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;
@@ -625,5 +741,25 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
     ctx->prof_n++;
   }
   PMX_LAUNCHED(ctx);
+  if (p.trace && getenv("PMX_TRACE_DUMP")) {  // debug: print the timeline of this launch
+    static int dumped = 0;
+    if (dumped++ == 3) {
+      long long h[5 * TRACE_TILES * TRACE_EVENTS];
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+      long long t0 = h[(0 * TRACE_TILES + 4) * TRACE_EVENTS + 0];
+      const char* roles[5] = {"producer", "issuer1", "issuer2", "residual", "flush"};
+      for (int t = 4; t < TRACE_TILES; ++t)
+        for (int r = 0; r < 5; ++r) {
+          printf("TRACE tile %2d %-9s", t, roles[r]);
+          for (int e = 0; e < TRACE_EVENTS; ++e) {
+            long long v = h[(r * TRACE_TILES + t) * TRACE_EVENTS + e];
+            printf(" %7lld", v ? v - t0 : -1);
+          }
+          printf("\n");
+        }
+      fflush(stdout);
+    }
+  }
   return pmx_check_launch(ctx, "k_grad_umma");
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # timing ablation of the fused gradient kernel (results are numerically meaningless, only kernel ms matters)
-for ab in 0 1 2 4 6 7 8 16 24 32 64 88 120 127; do
+for ab in "$@"; do
   PMX_ABLATE=$ab python bench.py --steps 30 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import sys, json
 for line in sys.stdin:
