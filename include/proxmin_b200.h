@@ -231,6 +231,9 @@ typedef enum {
 int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const float* c, const float* d, float s0,
            float s1, float* o0, float* o1, float* o2, double* red_host);
 
+/* sums along an axis of a device matrix: out_host has cols (axis 0) or rows (axis 1) doubles (nmf.py:91-93 means) */
+int pmx_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* out_host);
+
 /* adaprox building blocks on caller-owned device arrays (callback loop of algorithms.py:365-410).
  * alpha: mode 0 = scalar alpha_value, 2 = per-column vector alpha_dev[cols], 3 = per-row vector alpha_dev[rows]. */
 int pmx_adaprox_moments(pmx_ctx* ctx, int scheme, const float* G, float* M, float* V, float* Vhat_or_null, float* X,

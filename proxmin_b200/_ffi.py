@@ -123,6 +123,7 @@ def _declare(L):
         "pmx_admm_step": [vp, C.c_double, pi, pi, pd],
         "pmx_admm_run": [vp, C.c_double, i32, pi, pi, pd],
         "pmx_pgm_update": [vp, C.POINTER(Prox), vp, vp, vp, i32, i32, f32, pd, pd],
+        "pmx_axis_sum": [vp, vp, i32, i32, i32, pd],
         "pmx_ew": [vp, i32, sz, vp, vp, vp, vp, f32, f32, vp, vp, vp, pd],
         "pmx_adaprox_moments": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, f32, C.c_double, C.c_double,
                                 f32, f32, f32, i32, pf],

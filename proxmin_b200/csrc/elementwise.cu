@@ -52,6 +52,16 @@ __device__ __forceinline__ bool skip(const UpdIO& io) {
   return (io.done && *io.done) || (io.done2 && *io.done2);
 }
 
+__device__ __forceinline__ void store_split(const UpdIO& io, int r, int c, float v) {
+  if (io.hi) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t j = (size_t)r * io.ld_split + c;
+    io.hi[j] = __bfloat16_as_ushort(h);
+    io.lo[j] = __bfloat16_as_ushort(l);
+  }
+}
+
 // the value the prox chain starts from, and the step handed to the chain
 template <int IN>
 __device__ __forceinline__ float transform(const UpdIO& io, size_t i, int r, int c, float& pstep) {
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
   if (skip(io)) return;
   const size_t n = (size_t)io.rows * io.cols;
   float nd = 0.f, nn = 0.f, np = 0.f;
-  const bool need_rc = io.step.mode >= 2;
+  const bool need_rc = io.step.mode >= 2 || io.hi != nullptr;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0, c = 0;
     if (need_rc) {
@@ -96,6 +106,7 @@ __global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
     v = chain_segment(ch, 0, ch.n, v, ps);
     if (io.Xold_out) io.Xold_out[i] = prev;
     io.Xout[i] = v;
+    store_split(io, r, c, v);
     const float d = v - prev;
     nd += d * d;
     nn += v * v;
@@ -107,12 +118,71 @@ __global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
 // ---- chains with UNITY(axis=0): one thread owns a column (coalesced across threads) -----
 // Rows are processed in batches of RB with all loads issued before the arithmetic, so that a thread
 // keeps RB x (number of input streams) requests in flight: the pass is latency-bound otherwise.
+// Fast path for short columns (rows <= 64, i.e. S with K <= 64) and a chain that ENDS with its only UNITY
+// (prox_unity, prox_unity_plus): the column stays in registers between the sum and the division, so S is
+// read once and written once (4 HBM streams instead of 7).
+template <int IN>
+__global__ void __launch_bounds__(128) k_upd_cols_reg(ProxChain ch, UpdIO io) {
+  if (skip(io)) return;
+  constexpr int RMAX = 64;
+  float nd = 0.f, nn = 0.f, np = 0.f;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < io.cols) {
+    const bool prev_is_in = (io.Xprev == io.Xin);
+    const int b = ch.n - 1;   // position of the UNITY op
+    float t[RMAX], pv[RMAX];
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < io.rows) {
+        const size_t i = (size_t)r * io.cols + c;
+        const float xin = io.Xin[i];
+        const float g = (IN != IN_PLAIN) ? io.G[i] : 0.f;
+        const float x0 = (IN == IN_ADASUB) ? io.X0[i] : 0.f;
+        pv[r] = prev_is_in ? xin : (io.Xprev ? io.Xprev[i] : 0.f);
+        const float s = step_at(io.step, r, c);
+        float ps = s, v;
+        if (IN == IN_PGM) {
+          v = __fsub_rn(xin, __fmul_rn(s, g));
+        } else if (IN == IN_ADASUB) {
+          const float gamma = s / io.psimax[0];
+          ps = gamma;
+          v = xin - gamma / s * g * (xin - x0);
+        } else {
+          v = xin;
+        }
+        v = chain_segment(ch, 0, b, v, ps);
+        t[r] = v;
+        sum += v;   // row order, like NumPy's axis-0 reduction
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < io.rows) {
+        const size_t i = (size_t)r * io.cols + c;
+        const float v = t[r] / sum;                      // operators.py:44
+        if (io.Xold_out) io.Xold_out[i] = pv[r];
+        io.Xout[i] = v;
+        store_split(io, r, c, v);
+        const float d = v - pv[r];
+        nd += d * d; nn += v * v; np += pv[r] * pv[r];
+      }
+    }
+  }
+  if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+}
+
 template <int IN>
 __global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
   if (skip(io)) return;
   constexpr int RB = 8;
+  extern __shared__ __align__(16) float gtile[];   // [rows][GLD] final values of this block's 128 columns (Gram fusion)
+  constexpr int GLD = 129;
+  const bool want_gram = io.gram_part != nullptr;
   float nd = 0.f, nn = 0.f, np = 0.f;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (want_gram && c >= io.cols)
+    for (int r = 0; r < io.rows; ++r) gtile[r * GLD + threadIdx.x] = 0.f;
   if (c < io.cols) {
     const bool alias = (io.Xprev == io.Xout);
     const float* prev_src = alias ? io.Xold_out : io.Xprev;
@@ -154,6 +224,8 @@ __global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
           io.Xout[i] = v;
           sum += v;
           if (b >= ch.n) {
+            store_split(io, r, c, v);
+            if (want_gram) gtile[r * GLD + threadIdx.x] = v;
             const float d = v - prev[j];
             nd += d * d; nn += v * v; np += prev[j] * prev[j];
           }
@@ -188,6 +260,8 @@ __global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
             io.Xout[i] = v;
             sum += v;
             if (last) {
+              store_split(io, r, c, v);
+              if (want_gram) gtile[r * GLD + threadIdx.x] = v;
               const float d = v - prev[j];
               nd += d * d; nn += v * v; np += prev[j] * prev[j];
             }
@@ -197,6 +271,33 @@ __global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
     }
   }
   if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+  if (want_gram) {
+    // block partial of X X^T over this block's 128 columns: thread -> 4 x 8 outputs (rows <= 64)
+    __syncthreads();
+    const int i0 = (threadIdx.x >> 3) * 4, j0 = (threadIdx.x & 7) * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
+    for (int cc = 0; cc < 128; ++cc) {
+      float av[4], bv[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) av[p] = (i0 + p < io.rows) ? gtile[(i0 + p) * GLD + cc] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bv[q] = (j0 + q < io.rows) ? gtile[(j0 + q) * GLD + cc] : 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+    }
+    float* out = io.gram_part + (size_t)blockIdx.x * io.rows * io.rows;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (i0 + p < io.rows && j0 + q < io.rows) out[(i0 + p) * io.rows + j0 + q] = acc[p][q];
+  }
 }
 
 // ---- chains with UNITY(axis=1): one warp owns a row ------------------------------------
@@ -221,6 +322,7 @@ __global__ void __launch_bounds__(kThreads) k_upd_rows(ProxChain ch, UpdIO io) {
       io.Xout[i] = v;
       sum += v;
       if (b >= ch.n) {
+        store_split(io, r, c, v);
         const float d = v - prev;
         nd += d * d; nn += v * v; np += prev * prev;
       }
@@ -237,6 +339,7 @@ __global__ void __launch_bounds__(kThreads) k_upd_rows(ProxChain ch, UpdIO io) {
         io.Xout[i] = v;
         sum += v;
         if (b >= ch.n) {
+          store_split(io, r, c, v);
           const float prev = prev_src ? prev_src[i] : 0.f;
           const float d = v - prev;
           nd += d * d; nn += v * v; np += prev * prev;
@@ -260,13 +363,26 @@ int launch_update_t(pmx_ctx* ctx, const ProxChain& chain, const UpdIO& io) {
     pmx_set_error("in-place UNITY update with norms needs an Xold buffer");
     return PMX_ERR_ARG;
   }
+  if (io.gram_part && !(ax == 0 && io.rows <= 64)) {
+    pmx_set_error("fused Gram output needs the column-owner kernel (UNITY axis 0) and rows <= 64");
+    return PMX_ERR_ARG;
+  }
   if (ax == -1) {
     long long blocks = (long long)((n + kThreads - 1) / kThreads);
     const long long cap = (long long)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     k_upd_flat<IN><<<(int)blocks, kThreads, 0, ctx->stream>>>(chain, io);
   } else if (ax == 0) {
-    k_upd_cols<IN><<<pmx_div_up(io.cols, 128), 128, 0, ctx->stream>>>(chain, io);
+    int n_unity = 0;
+    for (int i = 0; i < chain.n; ++i) n_unity += chain.op[i] == PMX_OP_UNITY;
+    // the register-resident variant measured 4x slower than the two-pass kernel on B200 (204 vs 53 us for
+    // S = 64 x 65536): kept for reference, disabled
+    const bool reg_path = false && io.rows <= 64 && n_unity == 1 && chain.op[chain.n - 1] == PMX_OP_UNITY;
+    if (reg_path)
+      k_upd_cols_reg<IN><<<pmx_div_up(io.cols, 128), 128, 0, ctx->stream>>>(chain, io);
+    else
+      k_upd_cols<IN><<<pmx_div_up(io.cols, 128), 128, io.gram_part ? sizeof(float) * io.rows * 129 : 0,
+                       ctx->stream>>>(chain, io);
   } else {
     const int wpb = kThreads / 32;
     long long blocks = pmx_div_up(io.rows, wpb);

@@ -156,6 +156,26 @@ int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const
   return st;
 }
 
+// sums along an axis of a device matrix (np.mean / np.sum building block, nmf.py:91-93); out_host: cols (axis 0) or rows (axis 1) doubles
+int pmx_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* out_host) {
+  PMX_REQUIRE(ctx && X && out_host, "NULL argument");
+  PMX_REQUIRE(axis == 0 || axis == 1, "axis must be 0 or 1");
+  const int n = axis == 0 ? cols : rows;
+  double* d = nullptr;
+  PMX_CUDA(cudaMalloc((void**)&d, sizeof(double) * (n ? n : 1)));
+  int st = launch_axis_sum(ctx, X, rows, cols, axis, d, nullptr);
+  if (st == PMX_OK) {
+    cudaError_t err = cudaMemcpyAsync(out_host, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    if (err != cudaSuccess) {
+      pmx_set_error("pmx_axis_sum: %s", cudaGetErrorString(err));
+      st = PMX_ERR_CUDA;
+    }
+  }
+  cudaFree(d);
+  return st;
+}
+
 // adaprox moment update + step on caller-owned device arrays (algorithms.py:147-245, :378); *psimax_host = max(Psi)
 int pmx_adaprox_moments(pmx_ctx* ctx, int scheme, const float* G, float* M, float* V, float* Vhat_or_null, float* X,
                         float* Psi, int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value,

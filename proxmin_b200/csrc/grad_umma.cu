@@ -683,6 +683,10 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   PMX_CUDA(cudaMalloc(&pl->Alo, (size_t)pl->Mp * KP * 2));
   PMX_CUDA(cudaMalloc(&pl->Shi, (size_t)KP * pl->Np * 2));
   PMX_CUDA(cudaMalloc(&pl->Slo, (size_t)KP * pl->Np * 2));
+  PMX_CUDA(cudaMemsetAsync(pl->Ahi, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Alo, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Shi, 0, (size_t)KP * pl->Np * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Slo, 0, (size_t)KP * pl->Np * 2, ctx->stream));
   // Y: fp32, box 32 columns x 128 rows; out-of-bounds rows/columns are zero-filled by TMA
   PMX_CHECK(make_map(&pl->tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldY * 4, Y_SUB, TILE_M));
   PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, KP, (uint64_t)pl->Mp, KP * 2, KP, TILE_M));
@@ -707,10 +711,16 @@ void umma_plan_destroy(UmmaPlan* pl) {
   delete pl;
 }
 
+void umma_plan_buffers(UmmaPlan* pl, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldS) {
+  *Ahi = pl->Ahi; *Alo = pl->Alo; *Shi = pl->Shi; *Slo = pl->Slo; *ldS = pl->Np;
+}
+
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done) {
-  PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
-  PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
+                     const int* done, int skip_split) {
+  if (!skip_split) {
+    PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
+    PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
+  }
   PMX_CHECK(launch_zero(ctx, ctx->stream, GA, (size_t)pl->M * pl->K, done));
   PMX_CHECK(launch_zero(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, done));
   if (loss) PMX_CHECK(launch_zero(ctx, ctx->stream, reinterpret_cast<float*>(loss), 2, done));

@@ -32,7 +32,7 @@ __device__ __forceinline__ void gram_block(const float* T, int len, int ldt, int
 
 // X is rows x cols row-major.  TALL: Gram (cols x cols) over rows.  !TALL: Gram (rows x rows) over cols.
 template <bool TALL>
-__global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int rows, int cols, double* __restrict__ gram,
+__global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int rows, int cols, float* __restrict__ part,
                                               const int* done) {
   if (done && *done) return;
   extern __shared__ __align__(16) float smem[];
@@ -84,9 +84,29 @@ __global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int r
       for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (i0 + p < C && j0 + q < C) atomicAdd(&gram[(size_t)(i0 + p) * C + (j0 + q)], (double)acc[u][p][q]);
+          if (i0 + p < C && j0 + q < C) part[(size_t)blockIdx.x * C * C + (size_t)(i0 + p) * C + (j0 + q)] = acc[u][p][q];
     }
   }
+}
+
+// gram[e] = sum over blocks of part[b][e], in fp64 (the per-block partial sums are fp32 over <= a few hundred terms)
+__global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int nblocks, int n, double* __restrict__ gram,
+                                                     const int* done) {
+  if (done && *done) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  // 8 independent partial sums keep 8 loads in flight per thread
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(b + u) * n + e];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] += (double)v[u];
+  }
+  for (; b < nblocks; ++b) acc[0] += (double)part[(size_t)b * n + e];
+  gram[e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 // One CTA (1024 threads).  gram: C x C fp64 (symmetric PSD).  which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].
@@ -246,6 +266,10 @@ __global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ 
 
 }  // namespace
 
+// scratch for the per-block partial Gram matrices: one buffer per (context, tall/wide), grown on demand
+static float* g_part[2] = {nullptr, nullptr};
+static size_t g_part_bytes[2] = {0, 0};
+
 int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int cols, bool tall, double* gram,
                 const int* done) {
   const int C = tall ? cols : rows;
@@ -257,17 +281,25 @@ int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int col
   const int C4 = (C + 3) & ~3;
   const size_t smem = (size_t)kTileLen * (C4 + 4) * sizeof(float);
   long long nchunks = (L + kTileLen - 1) / kTileLen;
+  // enough blocks to keep loads in flight on every SM, few enough that the fp64 reduction stays tiny
   int blocks = (int)(nchunks < (long long)ctx->sm_count * 2 ? nchunks : (long long)ctx->sm_count * 2);
   if (blocks < 1) blocks = 1;
-  cudaError_t e = cudaMemsetAsync(gram, 0, sizeof(double) * C * C, st);
-  if (e != cudaSuccess) {
-    pmx_set_error("memset gram: %s", cudaGetErrorString(e));
-    return PMX_ERR_CUDA;
+  const int w = tall ? 1 : 0;
+  const size_t need = sizeof(float) * (size_t)blocks * C * C;
+  if (need > g_part_bytes[w]) {
+    if (g_part[w]) cudaFree(g_part[w]);
+    if (cudaMalloc((void**)&g_part[w], need) != cudaSuccess) {
+      pmx_set_error("cudaMalloc of the Gram scratch failed");
+      return PMX_ERR_CUDA;
+    }
+    g_part_bytes[w] = need;
   }
   if (tall)
-    k_gram<true><<<blocks, 256, smem, st>>>(X, rows, cols, gram, done);
+    k_gram<true><<<blocks, 256, smem, st>>>(X, rows, cols, g_part[w], done);
   else
-    k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, gram, done);
+    k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, g_part[w], done);
+  PMX_LAUNCHED(ctx);
+  k_gram_reduce<<<pmx_div_up(C * C, 256), 256, 0, st>>>(g_part[w], blocks, C * C, gram, done);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_gram");
 }
@@ -300,4 +332,11 @@ int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int w
   k_lambda_max<<<gram1 ? 2 : 1, 1024, smem, st>>>(gram0, which0, gram1, which1, C, ctl, 20);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_lambda_max");
+}
+
+// partial Gram matrices written by another kernel (fused S update): sum them into `gram` (fp64)
+int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nblocks, int C, double* gram, const int* done) {
+  k_gram_reduce<<<pmx_div_up(C * C, 256), 256, 0, st>>>(part, nblocks, C * C, gram, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_gram_reduce");
 }

@@ -9,6 +9,7 @@ int launch_split_bf16(pmx_ctx* ctx, const float* X, int rows, int cols, void* hi
                       const int* done);
 int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int cols, bool tall, double* gram,
                 const int* done);
+int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nblocks, int C, double* gram, const int* done);
 int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which);
 int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
                        int C, pmx_ctl* ctl);

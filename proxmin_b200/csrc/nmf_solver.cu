@@ -8,6 +8,7 @@
 // iteration where the reference would `break`, while the host polls the flag only every
 // `check_every` iterations.
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "grad_umma.h"
@@ -23,11 +24,17 @@ struct pmx_nmf {
   pmx_ctl* ctl;     // device
   pmx_ctl* h_ctl;   // pinned host mirror
   UmmaPlan* plan;   // tcgen05 gradient kernel state (tensor maps, bf16 operand buffers); lazily built
+  float* gram_part; // per-block partial Gram matrices of S written by the fused S update
+  bool gramS_valid; // gramS already holds S S^T of the current S (fused update): skip the standalone Gram pass
+  bool split_valid; // plan's bf16 operand buffers hold the split of the current (A, S) (written by the update kernels)
+  bool used_umma;   // the last gradient evaluation went through the tcgen05 kernel
   // ---- pgm
   pmx_pgm_opts pgm;
   ProxChain chA, chS;
   double nest_t;
   int it_enqueued;
+  cudaGraphExec_t pgm_graph;   // steady-state iteration captured once, replayed per iteration (no launch gaps)
+  long long pgm_graph_launches; // kernels inside the graph (for the launch counter)
   // ---- adaprox
   pmx_adaprox_opts ada;
   float *MA, *MS, *VA, *VS, *VhA, *VhS, *Psi, *Z0, *Z1, *alphaA, *alphaS;
@@ -84,8 +91,11 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
       return PMX_ERR_UNSUPPORTED;
     }
     if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
-    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done));
+    const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
+    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip));
+    h->used_umma = true;
   } else {
+    h->used_umma = false;
     PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, A, S, h->M, h->N, h->K, GA, GS, loss, done));
   }
   if (ctx->world > 1) {
@@ -101,7 +111,7 @@ int nmf_steps(pmx_nmf* h, const float* A, const float* S, bool need_A, bool need
   pmx_ctx* ctx = h->ctx;
   PMX_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-  if (need_A) {  // step for A needs the Gram of S (sum over this rank's columns, then over ranks)
+  if (need_A && !(h->gramS_valid && S == h->S)) {  // Gram of S: sum over this rank's columns, then over ranks
     PMX_CHECK(launch_gram(ctx, ctx->aux, S, h->K, h->N, false, h->gramS, &h->ctl->done));
     if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->aux));
   }
@@ -159,6 +169,7 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   cudaStreamSynchronize(h->ctx->aux);
+  if (h->gram_part) cudaFree(h->gram_part);
   float* bufs[] = {h->Y, h->A, h->S, h->A_old, h->S_old, h->Ae, h->Se, h->GA, h->GS, h->MA, h->MS, h->VA, h->VS,
                    h->VhA, h->VhS, h->Psi, h->Z0, h->Z1, h->alphaA, h->alphaS};
   for (float* b : bufs)
@@ -173,6 +184,7 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaFree(h->gramS);
   cudaFree(h->ctl);
   cudaFreeHost(h->h_ctl);
+  if (h->pgm_graph) cudaGraphExecDestroy(h->pgm_graph);
   if (h->plan) umma_plan_destroy(h->plan);
   delete h;
   return PMX_OK;
@@ -213,6 +225,10 @@ int pmx_nmf_set(pmx_nmf* h, int which, const float* host_src) {
   PMX_REQUIRE(h && host_src, "NULL argument");
   float* p; size_t n;
   PMX_CHECK(which_ptr(h, which, &p, &n));
+  if (which == PMX_A || which == PMX_S) {
+    h->split_valid = false;
+    h->gramS_valid = false;
+  }
   return pmx_h2d(h->ctx, p, host_src, n * sizeof(float));
 }
 
@@ -247,6 +263,12 @@ int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
 int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
   h->pgm = *opts;
+  h->split_valid = false;
+  h->gramS_valid = false;
+  if (h->pgm_graph) {
+    cudaGraphExecDestroy(h->pgm_graph);
+    h->pgm_graph = nullptr;
+  }
   if (h->pgm.check_every <= 0) h->pgm.check_every = 8;
   h->chA = make_chain(&opts->prox_A);
   h->chS = make_chain(&opts->prox_S);
@@ -291,13 +313,34 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   io.done = done;
   io.step.mode = 1;
   io.step.scale = 1.f;
+  // when the tcgen05 kernel is in use (and the next gradient is taken at (A, S) itself, i.e. no extrapolation) the
+  // update kernels also write the bf16 (hi, lo) operands of the next iteration's GEMMs
+  void *Ahi = nullptr, *Alo = nullptr, *Shi = nullptr, *Slo = nullptr;
+  int ldS = 0;
+  const bool fuse_split = h->used_umma && h->plan && !h->pgm.accelerated;
+  if (fuse_split) umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldS);
   io.Xin = Ae; io.G = h->GA; io.Xprev = h->A; io.Xout = h->A; io.Xold_out = h->A_old;
   io.norms = &h->ctl->norms[0]; io.rows = h->M; io.cols = h->K; io.step.ptr = &h->ctl->step[0];
+  io.hi = (unsigned short*)Ahi; io.lo = (unsigned short*)Alo; io.ld_split = 64;
   PMX_CHECK(launch_update(ctx, IN_PGM, h->chA, io));
   io.Xin = Se; io.G = h->GS; io.Xprev = h->S; io.Xout = h->S; io.Xold_out = h->S_old;
   io.norms = &h->ctl->norms[3]; io.rows = h->K; io.cols = h->N; io.step.ptr = &h->ctl->step[1];
+  io.hi = (unsigned short*)Shi; io.lo = (unsigned short*)Slo; io.ld_split = ldS;
+  // S S^T of the new S as a by-product of the update (column-owner kernel only): the next iteration's step_A
+  const bool fuse_gram = !h->pgm.accelerated && h->K <= 64 && chain_unity_axis(h->chS) == 0;
+  const int nblk = pmx_div_up(h->N, 128);
+  if (fuse_gram) {
+    if (!h->gram_part) PMX_CHECK(alloc_f(&h->gram_part, (size_t)nblk * h->K * h->K));
+    io.gram_part = h->gram_part;
+  }
   PMX_CHECK(launch_update(ctx, IN_PGM, h->chS, io));
-  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+  h->split_valid = fuse_split;
+  if (fuse_gram) PMX_CHECK(launch_gram_reduce(ctx, ctx->stream, h->gram_part, nblk, h->K, h->gramS, done));
+  h->gramS_valid = fuse_gram;
+  if (ctx->world > 1) {
+    PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+    if (fuse_gram) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->stream));
+  }
   const float eA = h->pgm.e_rel_A, eS = h->pgm.e_rel_S;
   k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, (float)((double)eA * (double)eA), (float)((double)eS * (double)eS));
   PMX_LAUNCHED(ctx);
@@ -311,8 +354,36 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
   PMX_CHECK(pull_ctl(h));
   const int it0 = h->h_ctl->it;
   bool stopped = h->h_ctl->done != 0;
+  static const bool no_graph = getenv("PMX_NO_GRAPH") != nullptr;
   for (int i = 0; i < n_iter && !stopped; ++i) {
-    PMX_CHECK(pgm_enqueue_iteration(h));
+    // Steady state (tcgen05 kernel, operands split by the update kernels, no extrapolation, no per-launch
+    // profiling): the iteration is a fixed kernel sequence on two streams (+ NCCL) -> replay it as a CUDA graph.
+    const bool steady = !no_graph && !h->ctx->profile && !h->pgm.accelerated && h->split_valid && h->used_umma &&
+                        h->it_enqueued >= 2;
+    if (steady) {
+      if (!h->pgm_graph) {
+        cudaGraph_t graph = nullptr;
+        const long long l0 = h->ctx->launches;
+        PMX_CUDA(cudaStreamBeginCapture(h->ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int st = pgm_enqueue_iteration(h);
+        cudaError_t ce = cudaStreamEndCapture(h->ctx->stream, &graph);
+        h->it_enqueued -= 1;               // the capture did not execute anything
+        h->pgm_graph_launches = h->ctx->launches - l0;
+        h->ctx->launches = l0;
+        if (st != PMX_OK) return st;
+        if (ce != cudaSuccess || !graph) {
+          pmx_set_error("CUDA graph capture of the PGM iteration failed: %s", cudaGetErrorString(ce));
+          return PMX_ERR_CUDA;
+        }
+        PMX_CUDA(cudaGraphInstantiate(&h->pgm_graph, graph, nullptr, nullptr, 0));
+        cudaGraphDestroy(graph);
+      }
+      PMX_CUDA(cudaGraphLaunch(h->pgm_graph, h->ctx->stream));
+      h->ctx->launches += h->pgm_graph_launches;
+      h->it_enqueued += 1;
+    } else {
+      PMX_CHECK(pgm_enqueue_iteration(h));
+    }
     if ((i + 1) % h->pgm.check_every == 0 && i + 1 < n_iter) {
       PMX_CHECK(pull_ctl(h));
       stopped = h->h_ctl->done != 0;
@@ -340,6 +411,8 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
     return PMX_ERR_UNSUPPORTED;
   }
   h->ada = *opts;
+  h->split_valid = false;
+  h->gramS_valid = false;
   h->chA = make_chain(&opts->prox_A);
   h->chS = make_chain(&opts->prox_S);
   const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
@@ -478,6 +551,8 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
     return PMX_ERR_UNSUPPORTED;
   }
   h->bs = *opts;
+  h->split_valid = false;
+  h->gramS_valid = false;
   const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
   const size_t big = mk > kn ? mk : kn;
   for (int j = 0; j < 2; ++j) {

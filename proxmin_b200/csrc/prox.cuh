@@ -104,6 +104,11 @@ struct UpdIO {
   const int* done;     // optional early-exit flag(s): skip when *done != 0
   const int* done2;
   const float* psimax; // IN_ADASUB: max(Psi) (algorithms.py:384)
+  unsigned short* hi;  // optional: bf16 (hi, lo) split of the result, element (r, c) at [r * ld_split + c]
+  unsigned short* lo;  //   (operands of the tcgen05 gradient GEMMs; saves the separate split pass)
+  int ld_split;
+  float* gram_part;    // optional (cols kernel, rows <= 64): per-block partial Gram  sum_c X[i,c] X[j,c]  of the result,
+                       //   [gridDim.x][rows*rows] -- the Lipschitz constant of the next iteration without another pass
   int rows, cols;
   StepSpec step;       // IN_PGM: step; IN_ADASUB: Alpha; IN_PLAIN: step handed to the prox
 };

@@ -230,10 +230,24 @@ def step_pgm(*X, it=None, W=1):
 
 
 def step_adaprox(*X, it=None):
-    """Per-component steps mean/10 (nmf.py:91-93).  Host helper for user code; the device adaprox loop
-    computes the same means with a reduction kernel."""
+    """Per-component steps mean/10 (nmf.py:91-93): column means of A (shape K) and row means of S (shape K x 1),
+    reduced on the device (the fused adaprox loop computes the same means inside the solver object)."""
     A, S = X
-    return (np.mean(A, axis=0) / 10, S.mean(axis=1)[:, None] / 10)
+    ctx = _ffi.context()
+    out = []
+    for X_, axis in ((A, 0), (S, 1)):
+        x32 = np.ascontiguousarray(X_, dtype=np.float32)
+        rows, cols = x32.shape
+        n = cols if axis == 0 else rows
+        d = ctx.upload(x32)
+        try:
+            sums = (C.c_double * n)()
+            _ffi.check(_ffi.lib().pmx_axis_sum(ctx.handle, d, rows, cols, axis, sums))
+        finally:
+            ctx.free(d)
+        mean = (np.array(sums[:]) / (rows if axis == 0 else cols)).astype(X_.dtype if X_.dtype.kind == "f" else np.float64)
+        out.append(mean)
+    return (out[0] / 10, out[1][:, None] / 10)
 
 
 def nmf(
