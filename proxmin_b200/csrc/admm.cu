@@ -38,6 +38,7 @@ struct PassArgs {
   int use_slack;
   int dual_uses_step_g;
   admm_ctl* ctl;
+  float* part;        // [gridDim.x][MAXG * 5] per-block partial norms (summed by k_admm_finalize: no same-address atomics)
 };
 
 __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
       if (threadIdx.x == 0) {
         float t = 0.f;
         for (int k = 0; k < kT / 32; ++k) t += red[k];
-        atomicAdd(&ctl->norms[i][q], (double)t);
+        a.part[(size_t)blockIdx.x * (MAXG * 5) + i * 5 + q] = t;
       }
     }
   const int any_x = __syncthreads_or(ch_x);
@@ -124,8 +125,26 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
 }
 
 // convergence test + iteration / restart state machine (algorithms.py:494-514)
-__global__ void k_admm_finalize(admm_ctl* ctl, int n_g, double n_elems, float e_rel, float e_abs, int manage) {
+__global__ void __launch_bounds__(256) k_admm_finalize(admm_ctl* ctl, int n_g, double n_elems, float e_rel, float e_abs,
+                                                       int manage, const float* part, int nblocks) {
   if (ctl->done) return;
+  // sum the per-block partial norms (fp64), 256 threads
+  __shared__ double s_acc[MAXG * 5][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int v = 0; v < n_g * 5; ++v) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += (double)part[(size_t)b * (MAXG * 5) + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_acc[v][w] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int v = 0; v < n_g * 5; ++v) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += s_acc[v][k];
+    ctl->norms[v / 5][v % 5] = t;
+  }
   bool all = true;
   for (int i = 0; i < n_g; ++i) {
     const float lLX = sqrtf((float)ctl->norms[i][0]);
@@ -172,6 +191,8 @@ __global__ void k_admm_finalize(admm_ctl* ctl, int n_g, double n_elems, float e_
 struct pmx_admm {
   pmx_ctx* ctx;
   size_t n;
+  float* part;
+  int nblocks;
   pmx_admm_opts opts;
   float *X, *b;
   float* Z[MAXG];
@@ -203,13 +224,11 @@ static int admm_enqueue(pmx_admm* h, double step_base, int use_slack, int manage
   a.use_slack = use_slack;
   a.dual_uses_step_g = h->opts.dual_uses_step_g;
   a.ctl = h->ctl;
-  long long blocks = (long long)((h->n + kT - 1) / kT);
-  const long long cap = (long long)ctx->sm_count * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  k_admm_pass<<<(int)blocks, kT, 0, ctx->stream>>>(a);
+  a.part = h->part;
+  k_admm_pass<<<h->nblocks, kT, 0, ctx->stream>>>(a);
   PMX_LAUNCHED(ctx);
-  k_admm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, h->opts.n_g, (double)h->n, h->opts.e_rel, h->opts.e_abs, manage);
+  k_admm_finalize<<<1, 256, 0, ctx->stream>>>(h->ctl, h->opts.n_g, (double)h->n, h->opts.e_rel, h->opts.e_abs, manage,
+                                              h->part, h->nblocks);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "admm pass");
 }
@@ -238,6 +257,14 @@ int pmx_admm_create(pmx_ctx* ctx, size_t n, const pmx_admm_opts* opts, pmx_admm*
     PMX_CUDA(cudaMalloc((void**)&h->Z[i], bytes));
     PMX_CUDA(cudaMalloc((void**)&h->U[i], bytes));
   }
+  {
+    long long blocks = (long long)((n + kT - 1) / kT);
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    h->nblocks = (int)blocks;
+  }
+  PMX_CUDA(cudaMalloc((void**)&h->part, sizeof(float) * (size_t)h->nblocks * MAXG * 5));
   PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(admm_ctl)));
   PMX_CUDA(cudaMallocHost((void**)&h->h_ctl, sizeof(admm_ctl)));
   *out = h;
@@ -253,6 +280,7 @@ int pmx_admm_destroy(pmx_admm* h) {
     if (h->Z[i]) cudaFree(h->Z[i]);
     if (h->U[i]) cudaFree(h->U[i]);
   }
+  cudaFree(h->part);
   cudaFree(h->ctl);
   cudaFreeHost(h->h_ctl);
   delete h;

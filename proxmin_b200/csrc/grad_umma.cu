@@ -22,8 +22,8 @@
 //   Y ring     4 x [128 m-rows][32 fp32]       64 KB   4 sub-tiles/tile  (TMA)
 // TMEM (512 columns): residual accumulator 2 x 128, G_S^T accumulator 2 x 64, G_A accumulator 64.
 //
-// Warp roles (512 threads): warp 0 = TMA producer, warps 1 and 3 = MMA issuers (residual + G_A / G_S),
-// warp 2 = TMEM allocator, warps 4..11 = residual warps (TMEM accumulator -> R in TMEM and SMEM; two warps
+// Warp roles (512 threads): warp 0 = TMA producer, warps 1, 2, 3 = MMA issuers (residual / G_A / G_S; warp 2
+// also allocates the tensor memory), warps 4..11 = residual warps (TMEM accumulator -> R in TMEM and SMEM; two warps
 // share each TMEM lane quarter and split the column chunks), warps 12..15 = gradient flush warps.
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -252,7 +252,9 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + OFF_BAR + 8 * B_COUNT);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then treats it (and every branch on it) as warp-uniform, which keeps
+  // the MMA issuers' descriptors and tensor-memory addresses in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // tile sequence: m-block major (all 128-column stripes of one 128-row block are consecutive)
@@ -320,15 +322,15 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer 1: residual GEMM and G_A GEMM ==============================
-    // Issue order per tile t:  MMA1(t+1) | MMA2(t).  All 32 lanes run this loop; one elected lane issues.
+    // ============================== MMA issuer 1: residual GEMM ==============================
+    // Three issuer warps (residual / G_A / G_S), each blocking only on its own dependencies; all 32 lanes run
+    // the loop and one elected lane issues.  MMA1(t+2) overwrites the accumulator whose columns hold R(t), the
+    // TMEM operand of MMA2(t): that hazard is ordered through the S slot -- S(t+2) is loaded only after MMA2(t)
+    // committed s_empty, and MMA1(t+2) waits for S(t+2).
     constexpr uint32_t ID_RES = make_idesc(128, 128, 0, 1);   // A tile K-major (SMEM), S tile MN-major
-    constexpr uint32_t ID_GA2 = make_idesc(128, 128, 0, 0);   // R_hi from TMEM x [S_hi;S_lo] K-major, N = 128
-    constexpr uint32_t ID_GA1 = make_idesc(128, 64, 0, 0);    // R_lo from TMEM x S_hi, N = 64
-    uint32_t seg_full = 0;
     const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
-
-    auto issue_residual = [&](long long g, uint32_t t) {
+    uint32_t t = 0, seg_full = 0;
+    for (long long g = g_begin; g < g_end; ++g, ++t) {
       const uint32_t slot = t & 1;
       mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);
       if (first_in_seg(g)) {
@@ -354,19 +356,19 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         }
       tc_commit_e(bar(B_ACC_FULL + slot));
       TR(1, t, 1);
-    };
-
-    // Blocking, in-order issue (a polling issuer that picks whichever stream is ready was measured slower: the
-    // spinning warp steals issue slots from the residual warps of its SM sub-partition).
+      if (last_in_seg(g)) tc_commit_e(bar(B_A_EMPTY));   // residual GEMMs of this segment are done with the A tile
+    }
+  } else if (warp == 2) {
+    // ============================== MMA issuer 2: G_A GEMM (after the TMEM allocation above) ================
+    // G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (K = n: 8 k-steps).  R (bf16 hi/lo)
+    // sits in the columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
+    constexpr uint32_t ID_GA2 = make_idesc(128, 128, 0, 0);   // R_hi from TMEM x [S_hi;S_lo] K-major, N = 128
+    constexpr uint32_t ID_GA1 = make_idesc(128, 64, 0, 0);    // R_lo from TMEM x S_hi, N = 64
     uint32_t t = 0, seg = 0;
-    if (g_begin < g_end) issue_residual(g_begin, 0);
     for (long long g = g_begin; g < g_end; ++g, ++t) {
-      const bool has_next = g + 1 < g_end;
-      if (has_next && !first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // look-ahead inside a segment
       const uint32_t slot = t & 1;
       const bool first = first_in_seg(g);
-      // G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (K = n: 8 k-steps).  R (bf16 hi/lo)
-      // sits in the columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
+      mbar_wait(bar(B_S_FULL + slot), (t >> 1) & 1);    // already complete (MMA1(t) consumed it): visibility only
       mbar_wait(bar(B_RT_FULL + slot), (t >> 1) & 1);
       if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
       tc_fence_after();
@@ -392,13 +394,11 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
       TR(1, t, 3);
       if (last_in_seg(g)) {
         tc_commit_e(bar(B_GA_FULL));
-        tc_commit_e(bar(B_A_EMPTY));        // residual GEMMs of this segment are done with the A tile
         ++seg;
       }
-      if (has_next && first_in_seg(g + 1)) issue_residual(g + 1, t + 1);  // new m-block: needs the new A tile
     }
   } else if (warp == 3) {
-    // ============================== MMA issuer 2: G_S GEMM ==============================
+    // ============================== MMA issuer 3: G_S GEMM ==============================
     // G_S^T[n, k] = R_hi^T A_hi + R_hi^T A_lo + R_lo^T A_hi   (M = n, N = k = 64, K = m: 8 k-steps), R^T from SMEM
     constexpr uint32_t ID_GS = make_idesc(128, 64, 1, 1);
     const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;

@@ -10,6 +10,9 @@
 //                    (reference: numpy.linalg.LinAlgError from eigvals, utils.py:34).
 #include "common.cuh"
 
+int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done);
+int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nblocks, int C, double* gram, const int* done);
+
 namespace {
 
 constexpr int kMaxK = 128;
@@ -89,24 +92,27 @@ __global__ void __launch_bounds__(256) k_gram(const float* __restrict__ X, int r
   }
 }
 
-// gram[e] = sum over blocks of part[b][e], in fp64 (the per-block partial sums are fp32 over <= a few hundred terms)
+// gram[e] += sum over a slice of the blocks of part[b][e], in fp64 (gram pre-zeroed; gridDim.y slices run in
+// parallel so that no thread walks more than ~32 partials; the per-block partials are fp32 sums of <= a few
+// hundred terms)
 __global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int nblocks, int n, double* __restrict__ gram,
                                                      const int* done) {
   if (done && *done) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  // 8 independent partial sums keep 8 loads in flight per thread
+  const int per = (nblocks + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(nblocks, b0 + per);
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int b = 0;
-  for (; b + 8 <= nblocks; b += 8) {
+  int b = b0;
+  for (; b + 8 <= b1; b += 8) {
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(b + u) * n + e];
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] += (double)v[u];
   }
-  for (; b < nblocks; ++b) acc[0] += (double)part[(size_t)b * n + e];
-  gram[e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  for (; b < b1; ++b) acc[0] += (double)part[(size_t)b * n + e];
+  if (b1 > b0) atomicAdd(&gram[e], ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
 }
 
 // One CTA (1024 threads).  gram: C x C fp64 (symmetric PSD).  which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].
@@ -299,9 +305,7 @@ int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int col
   else
     k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, g_part[w], done);
   PMX_LAUNCHED(ctx);
-  k_gram_reduce<<<pmx_div_up(C * C, 256), 256, 0, st>>>(g_part[w], blocks, C * C, gram, done);
-  PMX_LAUNCHED(ctx);
-  return pmx_check_launch(ctx, "k_gram");
+  return launch_gram_reduce(ctx, st, g_part[w], blocks, C, gram, done);
 }
 
 int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
@@ -336,7 +340,9 @@ int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int w
 
 // partial Gram matrices written by another kernel (fused S update): sum them into `gram` (fp64)
 int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nblocks, int C, double* gram, const int* done) {
-  k_gram_reduce<<<pmx_div_up(C * C, 256), 256, 0, st>>>(part, nblocks, C * C, gram, done);
+  PMX_CHECK(launch_zero(ctx, st, reinterpret_cast<float*>(gram), 2 * (size_t)C * C, done));
+  const int slices = nblocks >= 64 ? 16 : (nblocks >= 8 ? 4 : 1);
+  k_gram_reduce<<<dim3(pmx_div_up(C * C, 256), slices), 256, 0, st>>>(part, nblocks, C * C, gram, done);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_gram_reduce");
 }

@@ -36,7 +36,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // mode: 0 SS K/K N=128 | 1 SS A=K,B=MN N=128 | 2 SS K/K N=64 | 3 SS MN/MN N=64 | 4 TS B=K N=64 | 5 TS B=MN N=128
 //       6 SS MN/MN N=128 | 7 SS A=MN,B=K N=64 | 8 TS B=K N=128 | 9 SS K/K N=256
-__global__ void __launch_bounds__(128, 1) k_bench(int mode, int reps, long long* out) {
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k_bench(int reps, long long* out) {
+  constexpr int mode = MODE;
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar_storage;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(128, 1) k_bench(int mode, int reps, long long*
     uint32_t parity = 0;
     for (int rep = 0; rep < reps; ++rep) {
       const long long t0 = clock64();
+#pragma unroll
       for (int i = 0; i < 64; ++i) {
         const uint32_t ks = i & 7;
         switch (mode) {
@@ -93,11 +96,12 @@ int main() {
   long long* d;
   cudaMalloc(&d, 16 * sizeof(long long));
   cudaMemset(d, 0, 16 * sizeof(long long));
-  cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const char* names[] = {"SS K/K N=128", "SS A=K B=MN N=128", "SS K/K N=64", "SS MN/MN N=64", "TS B=K N=64", "TS B=MN N=128",
                          "SS MN/MN N=128", "SS A=MN B=K N=64", "TS B=K N=128", "SS K/K N=256"};
+  void (*kern[10])(int, long long*) = {k_bench<0>, k_bench<1>, k_bench<2>, k_bench<3>, k_bench<4>, k_bench<5>, k_bench<6>, k_bench<7>, k_bench<8>, k_bench<9>};
   for (int mode = 0; mode < 10; ++mode) {
-    k_bench<<<1, 128, 200 * 1024>>>(mode, 5, d);
+    cudaFuncSetAttribute(kern[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    kern[mode]<<<1, 128, 200 * 1024>>>(5, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
   }
