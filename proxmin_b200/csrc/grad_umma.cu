@@ -102,6 +102,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// TMA load with an L2 eviction-priority hint: Y is streamed once (evict_first) while the S / A operand tiles are
+// re-read by every m-block row / stripe (evict_last), so the 2 GB Y stream does not push them out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
+      : "memory");
+}
 // TMA prefetch of one box into L2 (no shared memory, no barrier): decouples the HBM latency from the ring depth
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
@@ -294,6 +314,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
     // ============================== TMA producer ==============================
     if (lane == 0) {
       uint32_t t = 0, seg = 0;
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      const bool hints = !(p.ablate & 128);
       for (long long g = g_begin; g < g_end; ++g, ++t) {
         const int mb = (int)(g / p.NS), stripe = (int)(g % p.NS);
         const int m0 = mb * TILE_M, n0 = stripe * TILE_N;
@@ -301,15 +323,25 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         mbar_wait(bar(B_S_EMPTY + slot), ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(bar(B_S_FULL + slot), 4 * PANEL_S);
         const uint32_t sb = base + OFF_S + slot * S_SLOT;
-        tma_load_2d(sb, &tmShi, n0, 0, bar(B_S_FULL + slot));
-        tma_load_2d(sb + PANEL_S, &tmSlo, n0, 0, bar(B_S_FULL + slot));
-        tma_load_2d(sb + S_PANEL, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot));
-        tma_load_2d(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot));
+        if (hints) {
+          tma_load_2d_hint(sb, &tmShi, n0, 0, bar(B_S_FULL + slot), pol_keep);
+          tma_load_2d_hint(sb + PANEL_S, &tmSlo, n0, 0, bar(B_S_FULL + slot), pol_keep);
+          tma_load_2d_hint(sb + S_PANEL, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot), pol_keep);
+          tma_load_2d_hint(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot), pol_keep);
+        } else {
+          tma_load_2d(sb, &tmShi, n0, 0, bar(B_S_FULL + slot));
+          tma_load_2d(sb + PANEL_S, &tmSlo, n0, 0, bar(B_S_FULL + slot));
+          tma_load_2d(sb + S_PANEL, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot));
+          tma_load_2d(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot));
+        }
         TR(0, t, 0);
         for (int q = 0; q < 4; ++q) {
           mbar_wait(bar(B_Y_EMPTY + q), (t & 1) ^ 1);
           mbar_expect_tx(bar(B_Y_FULL + q), PANEL_R);
-          tma_load_2d(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q));
+          if (hints)
+            tma_load_2d_hint(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q), pol_stream);
+          else
+            tma_load_2d(base + OFF_Y + q * PANEL_R, &tmY, n0 + q * Y_SUB, m0, bar(B_Y_FULL + q));
           TR(0, t, 1 + q);
         }
         if (first_in_seg(g)) {
