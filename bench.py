@@ -43,6 +43,19 @@ def dist_env():
     return world, rank, local
 
 
+def measured_traffic(M, n_loc, K, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_grad_umma launch from the committed ncu capture
+    (profiles/grad_umma_traffic.json); None when the capture is for another shape."""
+    p = os.path.join(ROOT, "profiles", "grad_umma_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    w = t.get("workload", {})
+    if (w.get("M"), w.get("N"), w.get("K")) != (M, n_loc, K):
+        return None
+    return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+
+
 def init_gloo(world, rank):
     if world == 1:
         return None
@@ -292,7 +305,7 @@ def run_product(args, world, rank, local):
         ach = alg / (avg_ms * 1e-3) / 1e9
         flops = 6.0 * M * n_loc * K
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "k_grad_umma", "avg_launch_ms": avg_ms, "launches_timed": kern_n,
+                "traffic": measured_traffic(M, n_loc, K, world), "kernel": "k_grad_umma", "avg_launch_ms": avg_ms, "launches_timed": kern_n,
                 "kernel_share_of_step": kern_ms / ms_prof, "peak_source": peak_src,
                 "timing": "per-launch CUDA events in a second pass of `steps` iterations (graph replay off)",
                 "algorithmic_bytes_per_launch": alg, "useful_tflops": flops / (avg_ms * 1e-3) / 1e12,

@@ -29,7 +29,9 @@ int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, 
 int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, int check);
 int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const float* G, float* const* Z, float* const* U,
                        float* T, double* sums_scratch, int rows, int cols, int n_g, const ProxChain& direct,
-                       const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs);
+                       const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs, bool sharded,
+                       double n_elems_global);
+int launch_alpha_from_sums(pmx_ctx* ctx, const double* sums, int n, double count, float* alpha, const int* done);
 int launch_bsdmm_iter_finalize(pmx_ctx* ctx, pmx_ctl* ctl);
 
 // elementwise.cu: adaprox moment update

@@ -18,6 +18,7 @@ int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind,
 struct pmx_nmf {
   pmx_ctx* ctx;
   int M, N, K;   // N = local number of columns (this rank's stripe of Y and S)
+  double N_global; // total number of columns over all ranks (row means of S in step_adaprox)
   int ldY;       // leading dimension of the device copy of Y (N rounded up to 4: TMA needs 16-byte row pitch)
   float *Y, *A, *S, *A_old, *S_old, *Ae, *Se, *GA, *GS;
   double *gramA, *gramS;
@@ -125,9 +126,30 @@ int nmf_steps(pmx_nmf* h, const float* A, const float* S, bool need_A, bool need
   PMX_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
   return PMX_OK;
 }
+int nmf_global_cols(pmx_nmf* h);
 int nmf_steps_join(pmx_nmf* h) {
   PMX_CUDA(cudaStreamWaitEvent(h->ctx->stream, h->ctx->ev_join, 0));
   return PMX_OK;
+}
+
+// total number of columns over all ranks (one tiny all-reduce; cached)
+int nmf_global_cols(pmx_nmf* h) {
+  h->N_global = (double)h->N;
+  if (h->ctx->world <= 1) return PMX_OK;
+  double* d = nullptr;
+  PMX_CUDA(cudaMalloc((void**)&d, sizeof(double)));
+  PMX_CUDA(cudaMemcpyAsync(d, &h->N_global, sizeof(double), cudaMemcpyHostToDevice, h->ctx->stream));
+  int st = pmx_comm_allreduce_internal(h->ctx, d, 1, 1, h->ctx->stream);
+  if (st == PMX_OK) {
+    cudaError_t e = cudaMemcpyAsync(&h->N_global, d, sizeof(double), cudaMemcpyDeviceToHost, h->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->ctx->stream);
+    if (e != cudaSuccess) {
+      pmx_set_error("nmf_global_cols: %s", cudaGetErrorString(e));
+      st = PMX_ERR_CUDA;
+    }
+  }
+  cudaFree(d);
+  return st;
 }
 
 extern "C" {
@@ -143,6 +165,7 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   h->N = N_local;
   h->K = K;
   h->ldY = (N_local + 3) & ~3;
+  h->N_global = (double)N_local;
   PMX_CUDA(cudaSetDevice(ctx->device));
   const size_t mk = (size_t)M * K, kn = (size_t)K * N_local;
   PMX_CHECK(alloc_f(&h->Y, (size_t)M * h->ldY));
@@ -406,10 +429,6 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
 int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
   PMX_REQUIRE(opts->scheme >= PMX_ADAM && opts->scheme <= PMX_RADAM, "unknown adaprox scheme");
-  if (h->ctx->world > 1) {
-    pmx_set_error("adaprox on a column-sharded problem is not implemented yet (single GPU only)");
-    return PMX_ERR_UNSUPPORTED;
-  }
   h->ada = *opts;
   h->split_valid = false;
   h->gramS_valid = false;
@@ -435,7 +454,17 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
   h->ada_it = 0;
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  PMX_CHECK(nmf_global_cols(h));
   return PMX_OK;
+}
+
+// row means of S over ALL columns (nmf.py:91-93): local row sums, all-reduce, divide by the global column count
+static int launch_alpha_means_global(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  double* sums = h->bs_norms + 128;
+  PMX_CHECK(launch_axis_sum(ctx, h->S, h->K, h->N, 1, sums, &h->ctl->done));
+  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, sums, (size_t)h->K, 1, ctx->stream));
+  return launch_alpha_from_sums(ctx, sums, h->K, h->N_global, h->alphaS, &h->ctl->done);
 }
 
 static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
@@ -474,6 +503,8 @@ static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
   a.b1 = b1; a.b1_prev = b1_prev; a.b2 = o.b2; a.eps = o.eps; a.p = o.p;
   a.t = it + 1;
   PMX_CHECK(launch_adaprox_moments(ctx, a));
+  // column-sharded S block: max(Psi) is a maximum over all ranks (algorithms.py:384)
+  if (j == 1 && ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &ctl->psi_max[1], 1, 2, ctx->stream));
   const bool has_prox = j == 0 ? o.has_prox_A : o.has_prox_S;
   if (!has_prox) return PMX_OK;   // algorithms.py:380
   const ProxChain& ch = j == 0 ? h->chA : h->chS;
@@ -498,6 +529,8 @@ static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
       io.rows = rows; io.cols = cols;
       io.step = alpha;
       PMX_CHECK(launch_update(ctx, IN_ADASUB, ch, io));
+      if (j == 1 && ctx->world > 1)   // the sub-iteration stop test is a global norm (algorithms.py:389)
+        PMX_CHECK(pmx_comm_allreduce_internal(ctx, &ctl->norms[8], 3, 1, ctx->stream));
       PMX_CHECK(launch_sub_finalize(ctx, ctl, e2, o.prox_max_iter));
     }
     PMX_CHECK(pull_ctl(h));
@@ -520,13 +553,14 @@ int pmx_nmf_adaprox_run(pmx_nmf* h, int n_iter, const double* b1, const double* 
     PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));   // algorithms.py:369
     if (o.step_mode == 0) {                                                                     // algorithms.py:370
       PMX_CHECK(launch_alpha_means(ctx, h->A, h->M, h->K, 0, h->bs_norms, h->alphaA, &h->ctl->done));
-      PMX_CHECK(launch_alpha_means(ctx, h->S, h->K, h->N, 1, h->bs_norms + 128, h->alphaS, &h->ctl->done));
+      PMX_CHECK(launch_alpha_means_global(h));
     }
     PMX_CHECK(adaprox_block(h, 0, it, b1[i], b1_prev[i]));
     PMX_CHECK(adaprox_block(h, 1, it, b1[i], b1_prev[i]));
     if (o.check_convergence) {   // algorithms.py:403-410
       PMX_CHECK(launch_diff_norms(ctx, h->A, h->A_old, (size_t)h->M * h->K, &h->ctl->norms[0], &h->ctl->done));
       PMX_CHECK(launch_diff_norms(ctx, h->S, h->S_old, (size_t)h->K * h->N, &h->ctl->norms[3], &h->ctl->done));
+      if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
     }
     const float eA = o.e_rel_A, eS = o.e_rel_S;
     PMX_CHECK(launch_adaprox_finalize(ctx, h->ctl, (float)((double)eA * eA), (float)((double)eS * eS), o.check_convergence));
@@ -546,10 +580,13 @@ int pmx_nmf_adaprox_run(pmx_nmf* h, int n_iter, const double* b1, const double* 
 int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
   PMX_REQUIRE(opts->n_g_A >= 0 && opts->n_g_A <= 4 && opts->n_g_S >= 0 && opts->n_g_S <= 4, "0..4 constraints per block");
-  if (h->ctx->world > 1) {
-    pmx_set_error("bsdmm on a column-sharded problem is not implemented yet (single GPU only)");
-    return PMX_ERR_UNSUPPORTED;
-  }
+  if (h->ctx->world > 1)
+    for (int i = 0; i < opts->n_g_S; ++i)
+      for (int k = 0; k < opts->proxs_g_S[i].n_ops; ++k)
+        if (opts->proxs_g_S[i].ops[k].op == PMX_OP_UNITY && opts->proxs_g_S[i].ops[k].axis == 1) {
+          pmx_set_error("prox_unity(axis=1) on the column-sharded S block needs a cross-rank row sum (not implemented)");
+          return PMX_ERR_UNSUPPORTED;
+        }
   h->bs = *opts;
   h->split_valid = false;
   h->gramS_valid = false;
@@ -571,6 +608,7 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
   PMX_CUDA(cudaMemsetAsync(h->bs_norms, 0, sizeof(double) * 256, h->ctx->stream));
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
   h->bs_it = 0;
+  PMX_CHECK(nmf_global_cols(h));
   return PMX_OK;
 }
 
@@ -594,12 +632,14 @@ int pmx_nmf_bsdmm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int*
     PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
     PMX_CHECK(nmf_steps_join(h));
     PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 0, h->A, h->GA, h->Zg[0], h->Ug[0], h->Z0, sums, h->M, h->K, o.n_g_A, dA,
-                                 gA, &h->ctl->step[0], h->bs_norms, o.e_rel_A, o.e_abs_A));
+                                 gA, &h->ctl->step[0], h->bs_norms, o.e_rel_A, o.e_abs_A, false,
+                                 (double)h->M * h->K));
     PMX_CHECK(nmf_steps(h, h->A, h->S, false, true));
     PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
     PMX_CHECK(nmf_steps_join(h));
     PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 1, h->S, h->GS, h->Zg[1], h->Ug[1], h->Z0, sums, h->K, h->N, o.n_g_S, dS,
-                                 gS, &h->ctl->step[1], h->bs_norms + 32, o.e_rel_S, o.e_abs_S));
+                                 gS, &h->ctl->step[1], h->bs_norms + 32, o.e_rel_S, o.e_abs_S, true,
+                                 (double)h->K * h->N_global));
     PMX_CHECK(launch_bsdmm_iter_finalize(ctx, h->ctl));
     if ((i + 1) % 8 == 0) PMX_CHECK(pull_ctl(h));
   }

@@ -2,6 +2,8 @@
 // (algorithms.py:365-410, :800-844; utils.py:295-391).  All are single coalesced passes.
 #include "kernels.h"
 
+int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
+
 namespace {
 
 constexpr int kT = 256;
@@ -323,6 +325,12 @@ int launch_alpha_means(pmx_ctx* ctx, const float* X, int rows, int cols, int axi
   return pmx_check_launch(ctx, "k_alpha_from_sums");
 }
 
+int launch_alpha_from_sums(pmx_ctx* ctx, const double* sums, int n, double count, float* alpha, const int* done) {
+  k_alpha_from_sums<<<1, 128, 0, ctx->stream>>>(sums, n, count, alpha, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_alpha_from_sums");
+}
+
 int launch_sub_begin(pmx_ctx* ctx, pmx_ctl* ctl, int block) {
   k_sub_begin<<<1, 1, 0, ctx->stream>>>(ctl, block);
   PMX_LAUNCHED(ctx);
@@ -347,7 +355,8 @@ int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, in
 // one block (j) of a bsdmm outer iteration; `g_unfused[i]` marks constraints whose chain contains UNITY
 int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const float* G, float* const* Z, float* const* U,
                        float* T, double* sums_scratch, int rows, int cols, int n_g, const ProxChain& direct,
-                       const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs) {
+                       const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs, bool sharded,
+                       double n_elems_global) {
   BsArgs a;
   memset(&a, 0, sizeof(a));
   a.X = X; a.G = G; a.T = T;
@@ -375,7 +384,9 @@ int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const fl
     k_bsdmm_zu<<<grid, kT, 0, ctx->stream>>>(a, i, fused ? 1 : 0);
     PMX_LAUNCHED(ctx);
   }
-  k_bsdmm_block_finalize<<<1, 1, 0, ctx->stream>>>(ctl, norms, n_g, (double)a.n, e_rel, e_abs, block);
+  if (sharded && ctx->world > 1)   // the S block is column-sharded: its norms are sums over the ranks
+    PMX_CHECK(pmx_comm_allreduce_internal(ctx, norms, (size_t)(n_g > 0 ? n_g * 5 : 5), 1, ctx->stream));
+  k_bsdmm_block_finalize<<<1, 1, 0, ctx->stream>>>(ctl, norms, n_g, n_elems_global, e_rel, e_abs, block);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "bsdmm block");
 }
