@@ -1,4 +1,4 @@
-"""Column-sharded solvers on N GPUs against the same problem solved on one GPU.
+"""Column-sharded solvers on N GPUs against the same problem solved by the oracle.
 
 Run under torchrun on a multi-GPU box (tests/test_gpu_parity.py::test_multi_gpu_sharded does so when >= 2 GPUs
 are visible):
@@ -6,36 +6,31 @@ are visible):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
         tests/mgpu_check.py
 
-Every rank builds the SAME seeded problem, keeps the columns workloads.shard_columns gives it and runs the
-solver on its stripe (Y, S sharded; A replicated; G_A, the Gram matrix of S, the S-block norms, max(Psi) and
-the row means of S all-reduced over NCCL).  Rank 0 then solves the whole problem alone (a second, local
-context-free Problem on the same GPU is not possible while the communicator is attached, so the single-GPU
-answer comes from the CPU oracle, the same checker the other GPU tests use) and compares.
+Every rank builds the SAME seeded problem, keeps the columns workloads.shard_columns gives it and calls the
+public ``nmf.nmf`` on its stripe (Y, S sharded; A replicated; G_A, the Gram matrix of S, the S-block norms,
+max(Psi) and the row sums of S all-reduced over NCCL).  Rank 0 solves the whole problem with the CPU oracle
+(the checker of every other GPU test) and compares the gathered factors and the iteration counts.
 """
 import os
 import sys
+from functools import partial
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+import apis  # noqa: E402
 import proxmin_b200 as pmx  # noqa: E402
 from proxmin_b200 import _ffi, workloads  # noqa: E402
-from proxmin_b200 import nmf as pnmf  # noqa: E402
 
 
 def relerr(a, b):
     return float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300))
-
-
-def gather_S(S_loc, N, world, rank):
-    parts = [None] * world
-    dist.all_gather_object(parts, S_loc)
-    return np.concatenate(parts, axis=1)
 
 
 def main():
@@ -46,76 +41,64 @@ def main():
     box = [ctx.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     pmx.init_distributed(box[0], world, rank)
-
-    from oracle import proxmin_oracle as orc   # checker only
-
-    M, N, K = 256, 1536 + 40, 16          # ragged last stripe
-    rng = np.random.RandomState(11)
-    A0 = rng.rand(M, K).astype(np.float32) + 0.1
-    S0 = rng.rand(K, N).astype(np.float32) + 0.1
-    Y = (A0 @ S0 + 0.01 * rng.rand(M, N)).astype(np.float32)
-    A1 = (A0 * (1 + 0.3 * rng.rand(M, K))).astype(np.float32)
-    S1 = (S0 * (1 + 0.3 * rng.rand(K, N))).astype(np.float32)
-    lo, hi = workloads.shard_columns(N, world, rank)
-    plus = [(_ffi.OP_PLUS, 0, 0, 0.0)]
+    prod, orc = apis.product(), apis.oracle()
     fails = []
 
-    def report(name, err, tol):
-        if rank == 0:
-            print("%-28s %.3e (tol %.0e) %s" % (name, err, tol, "ok" if err <= tol else "FAIL"), flush=True)
-            if not err <= tol:
-                fails.append(name)
+    def run(name, make, solve, tol, counts=True):
+        """make() -> (Y, A, S); solve(api, Y, A, S) updates A, S in place."""
+        Y, A, S = make()
+        N = Y.shape[1]
+        lo, hi = workloads.shard_columns(N, world, rank)
+        A_d, S_d = A.copy(), np.ascontiguousarray(S[:, lo:hi])
+        solve(prod, np.ascontiguousarray(Y[:, lo:hi]), A_d, S_d)
+        it_d = prod.iterations()
+        parts = [None] * world
+        dist.all_gather_object(parts, S_d)
+        As = [None] * world
+        dist.all_gather_object(As, A_d)
+        if rank != 0:
+            return
+        S_all = np.concatenate(parts, axis=1)
+        A_o, S_o = A.copy(), S.copy()
+        solve(orc, Y, A_o, S_o)
+        it_o = orc.iterations()
+        eA, eS = relerr(A_d, A_o), relerr(S_all, S_o)
+        rep = max(relerr(a, A_d) for a in As)          # A must be identical on all ranks
+        ok = eA <= tol and eS <= tol and rep == 0.0 and (not counts or it_d == it_o)
+        print("%-26s A %.2e S %.2e (tol %.0e) replicas %.1e iterations %s vs %s %s"
+              % (name, eA, eS, tol, rep, it_d, it_o, "ok" if ok else "FAIL"), flush=True)
+        if not ok:
+            fails.append(name)
 
-    # ---- PGM (both gradient kernels) --------------------------------------------------
-    import functools
-    for kern, kname in ((1, "simt"), (2, "tcgen05")):
-        prob = pnmf.Problem(np.ascontiguousarray(Y[:, lo:hi]), A1, np.ascontiguousarray(S1[:, lo:hi]))
-        prob.pgm_begin(plus, plus, False, (0.0, 0.0), kernel=kern, check_every=4)
-        it, _, _ = prob.pgm_run(12)
-        A_d, S_d = prob.get(_ffi.A), gather_S(prob.get(_ffi.S), N, world, rank)
-        prob.close()
-        if rank == 0:
-            A_o, S_o = A1.copy(), S1.copy()
-            orc.pgm([A_o, S_o], functools.partial(orc.nmf_grad, Y=Y), orc.nmf_step_pgm,
-                    prox=[orc.prox_plus, orc.prox_plus], max_iter=12, e_rel=0.0)
-            tol = 1e-5 if kern == 1 else 1e-4
-            report("pgm/%s A" % kname, relerr(A_d, A_o), tol)
-            report("pgm/%s S" % kname, relerr(S_d, S_o), tol)
-            if it != 12:
-                fails.append("pgm/%s iterations %d" % (kname, it))
+    def pgm_unity(api, Y, A, S):
+        api.nmf.nmf(Y, A, S, prox_A=api.prox_plus, prox_S=api.prox_unity_plus, max_iter=40, e_rel=0)
 
-    # ---- adaprox / amsgrad ------------------------------------------------------------
-    prob = pnmf.Problem(np.ascontiguousarray(Y[:, lo:hi]), A1, np.ascontiguousarray(S1[:, lo:hi]))
-    prob.adaprox_begin(plus, plus, "amsgrad", 0.999, 1e-8, 0.25, (1e-3, 1e-3), False, 1000)
-    n_it = 8
-    b1 = np.full(n_it, 0.9)
-    b1p = np.roll(b1, 1)
-    it, _, sub = prob.adaprox_run(n_it, b1, b1p)
-    A_d, S_d = prob.get(_ffi.A), gather_S(prob.get(_ffi.S), N, world, rank)
-    prob.close()
-    if rank == 0:
-        A_o, S_o = A1.copy(), S1.copy()
-        res = orc.adaprox([A_o, S_o], functools.partial(orc.nmf_grad, Y=Y), orc.nmf_step_adaprox,
-                          prox=[orc.prox_plus, orc.prox_plus], scheme="amsgrad", max_iter=n_it, e_rel=1e-3,
-                          check_convergence=False, return_counts=True) if "return_counts" in orc.adaprox.__code__.co_varnames \
-            else orc.adaprox([A_o, S_o], functools.partial(orc.nmf_grad, Y=Y), orc.nmf_step_adaprox,
-                             prox=[orc.prox_plus, orc.prox_plus], scheme="amsgrad", max_iter=n_it, e_rel=1e-3,
-                             check_convergence=False)
-        report("adaprox A", relerr(A_d, A_o), 2e-4)
-        report("adaprox S", relerr(S_d, S_o), 2e-4)
-        print("adaprox iterations", it, "sub-iterations", sub, "oracle", res, flush=True)
+    def pgm_converge(api, Y, A, S):
+        api.nmf.nmf(Y, A, S, max_iter=1000)
 
-    # ---- bsdmm ------------------------------------------------------------------------
-    prob = pnmf.Problem(np.ascontiguousarray(Y[:, lo:hi]), A1, np.ascontiguousarray(S1[:, lo:hi]))
-    gA = [[(_ffi.OP_PLUS, 0, 0, 0.0)], [(_ffi.OP_UNITY, 0, 0, 0.0)]]
-    gS = [[(_ffi.OP_PLUS, 0, 0, 0.0)], [(_ffi.OP_SOFT, 1, 0, 0.01)]]
-    prob.bsdmm_begin([], [], gA, gS, (1e-3, 1e-3), (0.0, 0.0))
-    it, _ = prob.bsdmm_run(5)
-    A_d, S_d = prob.get(_ffi.A), gather_S(prob.get(_ffi.S), N, world, rank)
-    prob.close()
-    if rank == 0:
-        A_o, S_o = A1.copy(), S1.copy()
-        orc.nmf_bsdmm_reference(Y, A_o, S_o, max_iter=5) if hasattr(orc, "nmf_bsdmm_reference") else None
+    def ada_ams(api, Y, A, S):
+        api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", max_iter=30, check_convergence=False)
+
+    def ada_adam(api, Y, A, S):
+        api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="adam", max_iter=25, e_rel=1e-3)
+
+    def ada_unity(api, Y, A, S):
+        api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", prox_S=api.prox_unity_plus, max_iter=30,
+                    check_convergence=False)
+
+    def bsdmm(api, Y, A, S):
+        proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus, partial(api.prox_soft, thresh=0.01)]]
+        api.nmf.nmf(Y, A, S, algorithm=api.bsdmm, prox_A=api.prox_id, prox_S=api.prox_id, proxs_g=proxs_g,
+                    max_iter=6, e_rel=1e-6)
+
+    run("pgm plus/unity_plus", lambda: workloads.cfg2(128, 384 + 72, 16, seed=5), pgm_unity, 1e-4)
+    run("pgm converge (cfg1)", lambda: workloads.cfg1(), pgm_converge, 1e-4)
+    run("pgm K=64 tcgen05", lambda: workloads.cfg2(512, 2048, 64, seed=8), pgm_unity, 1e-4)
+    run("adaprox amsgrad", lambda: workloads.cfg2(128, 384 + 72, 16, seed=6), ada_ams, 2e-4)
+    run("adaprox amsgrad unity", lambda: workloads.cfg2(128, 384, 16, seed=6), ada_unity, 2e-4)
+    run("adaprox adam converge", lambda: workloads.cfg2(64, 192 + 40, 8, seed=7), ada_adam, 2e-4)
+    run("bsdmm", lambda: workloads.cfg5(96, 256 + 24, 8, seed=9), bsdmm, 5e-4)
+
     dist.barrier()
     if rank == 0:
         print("FAILS", fails, flush=True)

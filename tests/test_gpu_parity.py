@@ -6,6 +6,9 @@ Tolerances (stated per test): the device computes in fp32 with 3xBF16-split tens
 plus/hard/soft/max/min outputs must be identical wherever the reference value is not within
 1e-6*max|X| of the threshold; iteration and sub-iteration counts must match where stated.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -282,3 +285,18 @@ def test_full_size_properties():
     assert np.all(np.diff(losses) < 0), losses
     assert S.min() >= 0 and A.min() >= 0
     assert np.allclose(S.sum(axis=0), 1.0, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_sharded():
+    """Column-sharded PGM / adaprox / bsdmm over NCCL against the oracle (tests/mgpu_check.py); needs >= 2 GPUs."""
+    import subprocess
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(os.path.dirname(__file__), "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
