@@ -45,6 +45,9 @@ int pmx_device_count(int* count);
 int pmx_ctx_create(int device, pmx_ctx** out);
 int pmx_ctx_destroy(pmx_ctx* ctx);
 int pmx_ctx_sync(pmx_ctx* ctx);
+/* Solver handles take their device buffers from a per-context cache of freed blocks (a solve on host arrays then
+ * costs no cudaMalloc/cudaFree after the first one of a shape); this returns the cached blocks to the driver. */
+int pmx_ctx_trim(pmx_ctx* ctx);
 /* number of kernels this library has launched on the context since creation */
 int pmx_ctx_launch_count(pmx_ctx* ctx, long long* count);
 /* name/SM count/memory of the device behind the context */

@@ -82,6 +82,7 @@ def _declare(L):
         "pmx_ctx_create": [i32, C.POINTER(vp)],
         "pmx_ctx_destroy": [vp],
         "pmx_ctx_sync": [vp],
+        "pmx_ctx_trim": [vp],
         "pmx_ctx_launch_count": [vp, C.POINTER(C.c_longlong)],
         "pmx_ctx_device_info": [vp, C.c_char_p, i32, pi, C.POINTER(sz)],
         "pmx_ctx_profile": [vp, i32],
@@ -172,6 +173,10 @@ class Context:
 
     def sync(self):
         check(lib().pmx_ctx_sync(self.handle))
+
+    def trim(self):
+        """Give the device blocks cached from destroyed solver handles back to the driver."""
+        check(lib().pmx_ctx_trim(self.handle))
 
     def launches(self):
         n = C.c_longlong(0)

@@ -1,6 +1,8 @@
 // extern "C" surface of libproxmin_b200.so: context, memory, standalone operators.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "kernels.h"
 
 static thread_local char g_err[1024] = "";
@@ -23,6 +25,68 @@ int pmx_check_launch(pmx_ctx* ctx, const char* what) {
 }
 
 int pmx_comm_destroy_internal(pmx_ctx* ctx);
+
+// ------------------------------------------------------------------ cached device allocations
+namespace {
+struct DevBlock {
+  void* p;
+  size_t bytes;
+  bool used;
+};
+struct DevPool {
+  std::vector<DevBlock> blocks;
+};
+}  // namespace
+
+int pmx_dev_alloc(pmx_ctx* ctx, void** out, size_t bytes) {
+  if (bytes == 0) bytes = 4;
+  if (!ctx->pool) ctx->pool = new DevPool();
+  DevPool* pool = static_cast<DevPool*>(ctx->pool);
+  for (DevBlock& b : pool->blocks)
+    if (!b.used && b.bytes == bytes) {   // exact size: repeated solves of one shape reuse their buffers
+      b.used = true;
+      *out = b.p;
+      return PMX_OK;
+    }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // give the cached blocks back and retry once
+    cudaGetLastError();
+    pmx_dev_trim(ctx);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pmx_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return PMX_ERR_CUDA;
+  }
+  pool->blocks.push_back({p, bytes, true});
+  *out = p;
+  return PMX_OK;
+}
+
+void pmx_dev_free(pmx_ctx* ctx, void* p) {
+  if (!p) return;
+  DevPool* pool = static_cast<DevPool*>(ctx->pool);
+  if (pool)
+    for (DevBlock& b : pool->blocks)
+      if (b.p == p) {
+        b.used = false;
+        return;
+      }
+  cudaFree(p);   // not ours
+}
+
+void pmx_dev_trim(pmx_ctx* ctx) {
+  DevPool* pool = static_cast<DevPool*>(ctx->pool);
+  if (!pool) return;
+  std::vector<DevBlock> keep;
+  for (DevBlock& b : pool->blocks) {
+    if (b.used) keep.push_back(b);
+    else cudaFree(b.p);
+  }
+  pool->blocks.swap(keep);
+}
 
 extern "C" {
 
@@ -55,6 +119,8 @@ int pmx_ctx_create(int device, pmx_ctx** out) {
   PMX_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   PMX_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   PMX_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  PMX_CUDA(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
+  PMX_CUDA(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
   PMX_CUDA(cudaEventCreate(&c->ev_t0));
   PMX_CUDA(cudaEventCreate(&c->ev_t1));
   PMX_CUDA(cudaMallocHost((void**)&c->h_flags, 256));
@@ -70,16 +136,27 @@ int pmx_ctx_destroy(pmx_ctx* ctx) {
   pmx_comm_destroy_internal(ctx);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
+  cudaEventDestroy(ctx->ev_fork2);
+  cudaEventDestroy(ctx->ev_join2);
   cudaEventDestroy(ctx->ev_t0);
   cudaEventDestroy(ctx->ev_t1);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
   cudaFreeHost(ctx->h_flags);
+  pmx_dev_trim(ctx);
+  delete static_cast<DevPool*>(ctx->pool);
   if (ctx->prof_ev) {
     for (int i = 0; i < 2 * PMX_PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete[] ctx->prof_ev;
   }
   delete ctx;
+  return PMX_OK;
+}
+
+int pmx_ctx_trim(pmx_ctx* ctx) {
+  PMX_REQUIRE(ctx != nullptr, "NULL context");
+  PMX_CUDA(cudaSetDevice(ctx->device));
+  pmx_dev_trim(ctx);
   return PMX_OK;
 }
 

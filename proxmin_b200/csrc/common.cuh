@@ -58,7 +58,7 @@ struct pmx_ctx {
   int sm_count;
   cudaStream_t stream;   // main stream: every kernel of the hot path
   cudaStream_t aux;      // side stream: Gram / lambda_max overlap with the gradient kernel
-  cudaEvent_t ev_fork, ev_join, ev_t0, ev_t1;
+  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2, ev_t0, ev_t1;
   long long launches;
   // NCCL (dlopen'ed lazily)
   void* nccl_comm;
@@ -71,6 +71,7 @@ struct pmx_ctx {
   int* h_flags;          // pinned host mirror for polled device flags
   char dev_name[128];
   size_t total_mem;
+  void* pool;            // cache of freed device blocks (pmx_dev_alloc / pmx_dev_free), see api.cu
 };
 
 static inline int pmx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -79,3 +80,10 @@ static inline int pmx_div_up(long long a, long long b) { return (int)((a + b - 1
 #define PMX_PROF_MAX 4096
 
 int pmx_check_launch(pmx_ctx* ctx, const char* what);
+
+// Device memory for solver handles goes through a per-context cache of freed blocks: a solve on host arrays
+// (create -> iterate -> destroy) then costs no cudaMalloc/cudaFree after the first one of a given shape (freeing and
+// re-mapping the 2 GB Y buffer was measured at 5-700 ms).  pmx_ctx_trim releases the cached blocks.
+int pmx_dev_alloc(pmx_ctx* ctx, void** p, size_t bytes);
+void pmx_dev_free(pmx_ctx* ctx, void* p);
+void pmx_dev_trim(pmx_ctx* ctx);

@@ -300,6 +300,187 @@ __global__ void __launch_bounds__(128) k_upd_cols(ProxChain ch, UpdIO io) {
   }
 }
 
+// ---- UNITY(axis=0) chains on short columns (rows <= 64: S with K <= 64) ---------------------
+// Tile = 32 columns x 64 rows, 256 threads = 32 columns x 8 row groups (a warp reads one 128-byte line per row).
+// Every thread first issues all its loads (8 rows x up to 3 streams), the column sums are taken by one warp in
+// NumPy's row order from a shared-memory copy of the tile, and the column never leaves the registers between the
+// sum and the division: S is read once and written once.  Blocks are persistent over a strided tile sequence so
+// that the fused Gram partial (X X^T over the block's columns, 4 x 4 outputs per thread, packed fp32x2 FMAs) is
+// written once per block.  The kernel is issue-bound, so the prox chain is decoded once per op for the thread's
+// eight elements instead of once per element.
+constexpr int CT_COLS = 32, CT_RPT = 8, CT_LD = 68;   // tile stored column-major: tileT[col][row], ld 68
+
+// ops [a, b) of the chain applied to N values that share the step (or have per-value steps when `ps` varies)
+template <int N>
+__device__ __forceinline__ void chain_segment_vec(const ProxChain& c, int a, int b, float (&v)[N], const float (&ps)[N]) {
+  for (int i = a; i < b; ++i) {
+    const int op = c.op[i];
+    const float thr = c.thr[i];
+    const bool rel = c.rel[i] != 0;
+    if (op == PMX_OP_PLUS) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = (v[j] < 0.0f) ? 0.0f : v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = prox_elem(v[j], op, rel ? __fmul_rn(thr, ps[j]) : thr);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+template <int IN>
+__global__ void __launch_bounds__(256, 3) k_upd_cols_tile(ProxChain ch, UpdIO io, int n_tiles) {
+  if (skip(io)) return;
+  __shared__ __align__(16) float tileT[CT_COLS * CT_LD];
+  __shared__ __align__(16) float tileD[CT_COLS * 2 * CT_LD];   // every value twice (a, a): broadcast operand of fp32x2 FMAs
+  __shared__ float colsum[CT_COLS];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const bool want_gram = io.gram_part != nullptr;
+  const bool prev_is_in = (io.Xprev == io.Xin);
+  const int rows = io.rows, cols = io.cols;
+  float nd = 0.f, nn = 0.f, np = 0.f;
+  // Gram outputs of this thread: rows gi0..gi0+3 x columns gj0..gj0+3 of the rows x rows matrix
+  const int gi0 = (threadIdx.x >> 4) * 4, gj0 = (threadIdx.x & 15) * 4;
+  unsigned long long acc[4][2];   // acc[p][h] = (G[gi0+p][gj0+2h], G[gi0+p][gj0+2h+1])
+#pragma unroll
+  for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = 0ull;
+  const int r0 = rg * CT_RPT;
+  const float step_scalar = (io.step.mode <= 1) ? step_at(io.step, 0, 0) : 0.f;
+  const float inv_psimax = 0.f;
+  (void)inv_psimax;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int c = tile * CT_COLS + cx;
+    const bool col_ok = c < cols;
+    const size_t i0 = (size_t)r0 * cols + (col_ok ? c : 0);
+    float xin[CT_RPT], g[CT_RPT], x0[CT_RPT], v[CT_RPT], ps[CT_RPT];
+    {
+      const float* pin = io.Xin + i0;
+      const float* pg = io.G + i0;
+      const float* p0 = io.X0 + i0;
+#pragma unroll
+      for (int j = 0; j < CT_RPT; ++j) {
+        const bool ok = col_ok && (r0 + j < rows);
+        xin[j] = ok ? pin[(size_t)j * cols] : 0.f;
+        g[j] = (IN != IN_PLAIN && ok) ? pg[(size_t)j * cols] : 0.f;
+        x0[j] = (IN == IN_ADASUB && ok) ? p0[(size_t)j * cols] : 0.f;
+      }
+    }
+    int a = 0, b = chain_next_unity(ch, 0);
+    const float psimax = (IN == IN_ADASUB) ? io.psimax[0] : 1.f;
+#pragma unroll
+    for (int j = 0; j < CT_RPT; ++j) {
+      const int r = r0 + j;
+      const float s = (io.step.mode <= 1) ? step_scalar : step_at(io.step, r < rows ? r : 0, col_ok ? c : 0);
+      if (IN == IN_PGM) {
+        ps[j] = s;
+        v[j] = __fsub_rn(xin[j], __fmul_rn(s, g[j]));
+      } else if (IN == IN_ADASUB) {
+        const float gamma = s / psimax;
+        ps[j] = gamma;
+        v[j] = xin[j] - gamma / s * g[j] * (xin[j] - x0[j]);
+      } else {
+        ps[j] = s;
+        v[j] = xin[j];
+      }
+    }
+    chain_segment_vec<CT_RPT>(ch, a, b, v, ps);
+#pragma unroll
+    for (int j = 0; j < CT_RPT; ++j)
+      if (!(col_ok && r0 + j < rows)) v[j] = 0.f;
+    while (b < ch.n) {   // one round per UNITY op: column sum in row order, divide, next elementwise segment
+      __syncthreads();   // previous readers of tileT are done
+      *reinterpret_cast<float4*>(&tileT[cx * CT_LD + r0]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&tileT[cx * CT_LD + r0 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+      __syncthreads();
+      if (threadIdx.x < CT_COLS) {
+        float sum = 0.f;
+        const float4* col = reinterpret_cast<const float4*>(&tileT[cx * CT_LD]);
+        for (int r4 = 0; r4 < (rows + 3) / 4; ++r4) {   // rows beyond `rows` hold zeros; NumPy's axis-0 order
+          const float4 t = col[r4];
+          sum += t.x; sum += t.y; sum += t.z; sum += t.w;
+        }
+        colsum[cx] = sum;
+      }
+      __syncthreads();
+      const float denom = colsum[cx];
+      a = b + 1;
+      b = chain_next_unity(ch, a);
+#pragma unroll
+      for (int j = 0; j < CT_RPT; ++j) v[j] = v[j] / denom;                 // operators.py:44
+      chain_segment_vec<CT_RPT>(ch, a, b, v, ps);
+#pragma unroll
+      for (int j = 0; j < CT_RPT; ++j)
+        if (!(col_ok && r0 + j < rows)) v[j] = 0.f;
+    }
+    // stores + norms
+    {
+      float* pout = io.Xout + i0;
+      float* pold = io.Xold_out ? io.Xold_out + i0 : nullptr;
+      const float* pprev = (!prev_is_in && io.Xprev) ? io.Xprev + i0 : nullptr;
+      unsigned short* phi = io.hi ? io.hi + (size_t)r0 * io.ld_split + c : nullptr;
+      unsigned short* plo = io.hi ? io.lo + (size_t)r0 * io.ld_split + c : nullptr;
+#pragma unroll
+      for (int j = 0; j < CT_RPT; ++j) {
+        if (col_ok && r0 + j < rows) {
+          const float prev = prev_is_in ? xin[j] : (pprev ? pprev[(size_t)j * cols] : 0.f);
+          if (pold) pold[(size_t)j * cols] = prev;
+          pout[(size_t)j * cols] = v[j];
+          if (phi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+            phi[(size_t)j * io.ld_split] = __bfloat16_as_ushort(h);
+            plo[(size_t)j * io.ld_split] = __bfloat16_as_ushort(l);
+          }
+          const float d = v[j] - prev;
+          nd = fmaf(d, d, nd); nn = fmaf(v[j], v[j], nn); np = fmaf(prev, prev, np);
+        }
+      }
+    }
+    if (want_gram) {
+      __syncthreads();
+      *reinterpret_cast<float4*>(&tileT[cx * CT_LD + r0]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&tileT[cx * CT_LD + r0 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+      float4* dd = reinterpret_cast<float4*>(&tileD[cx * 2 * CT_LD + 2 * r0]);
+      dd[0] = make_float4(v[0], v[0], v[1], v[1]);
+      dd[1] = make_float4(v[2], v[2], v[3], v[3]);
+      dd[2] = make_float4(v[4], v[4], v[5], v[5]);
+      dd[3] = make_float4(v[6], v[6], v[7], v[7]);
+      __syncthreads();
+#pragma unroll 4
+      for (int cc = 0; cc < CT_COLS; ++cc) {
+        const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&tileD[cc * 2 * CT_LD + 2 * gi0]);       // (a0,a0),(a1,a1)
+        const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&tileD[cc * 2 * CT_LD + 2 * gi0 + 4]);   // (a2,a2),(a3,a3)
+        const ulonglong2 bv = *reinterpret_cast<const ulonglong2*>(&tileT[cc * CT_LD + gj0]);                // (b0,b1),(b2,b3)
+        ffma2(acc[0][0], a01.x, bv.x); ffma2(acc[0][1], a01.x, bv.y);
+        ffma2(acc[1][0], a01.y, bv.x); ffma2(acc[1][1], a01.y, bv.y);
+        ffma2(acc[2][0], a23.x, bv.x); ffma2(acc[2][1], a23.x, bv.y);
+        ffma2(acc[3][0], a23.y, bv.x); ffma2(acc[3][1], a23.y, bv.y);
+      }
+    }
+  }
+  if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+  if (want_gram) {
+    float* out = io.gram_part + (size_t)blockIdx.x * rows * rows;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 f = *reinterpret_cast<const float2*>(&acc[p][h]);
+        if (gi0 + p < rows && gj0 + 2 * h < rows) out[(gi0 + p) * rows + gj0 + 2 * h] = f.x;
+        if (gi0 + p < rows && gj0 + 2 * h + 1 < rows) out[(gi0 + p) * rows + gj0 + 2 * h + 1] = f.y;
+      }
+  }
+}
+
 // ---- chains with UNITY(axis=1): one warp owns a row ------------------------------------
 template <int IN>
 __global__ void __launch_bounds__(kThreads) k_upd_rows(ProxChain ch, UpdIO io) {
@@ -350,6 +531,17 @@ __global__ void __launch_bounds__(kThreads) k_upd_rows(ProxChain ch, UpdIO io) {
   if (io.norms) block_accumulate3(nd, nn, np, io.norms);
 }
 
+}  // namespace
+
+// blocks the column-owner update kernel runs with (= number of fused Gram partials it writes)
+int upd_cols_blocks(pmx_ctx* ctx, int cols) {
+  const int n_tiles = pmx_div_up(cols, CT_COLS);
+  const int cap = ctx->sm_count * 3;
+  return n_tiles < cap ? n_tiles : cap;
+}
+
+namespace {
+
 template <int IN>
 int launch_update_t(pmx_ctx* ctx, const ProxChain& chain, const UpdIO& io) {
   const int ax = chain_unity_axis(chain);
@@ -378,7 +570,10 @@ int launch_update_t(pmx_ctx* ctx, const ProxChain& chain, const UpdIO& io) {
     // the register-resident variant measured 4x slower than the two-pass kernel on B200 (204 vs 53 us for
     // S = 64 x 65536): kept for reference, disabled
     const bool reg_path = false && io.rows <= 64 && n_unity == 1 && chain.op[chain.n - 1] == PMX_OP_UNITY;
-    if (reg_path)
+    if (io.rows <= 64) {
+      const int n_tiles = pmx_div_up(io.cols, CT_COLS);
+      k_upd_cols_tile<IN><<<upd_cols_blocks(ctx, io.cols), 256, 0, ctx->stream>>>(chain, io, n_tiles);
+    } else if (reg_path)
       k_upd_cols_reg<IN><<<pmx_div_up(io.cols, 128), 128, 0, ctx->stream>>>(chain, io);
     else
       k_upd_cols<IN><<<pmx_div_up(io.cols, 128), 128, io.gram_part ? sizeof(float) * io.rows * 129 : 0,
@@ -416,6 +611,46 @@ __global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ p4, size
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
+// up to three buffers in one launch (the gradient outputs and the loss of one gradient evaluation)
+struct ZeroArgs {
+  float* p[3];
+  size_t n[3];
+};
+__global__ void __launch_bounds__(kThreads) k_zero3(ZeroArgs a, const int* done) {
+  if (done && *done) return;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    float* p = a.p[b];
+    const size_t n = a.n[b];
+    if (!p || n == 0) continue;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const size_t n4 = n / 4;
+      float4* p4 = reinterpret_cast<float4*>(p);
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (blockIdx.x == 0 && threadIdx.x < n - n4 * 4) p[n4 * 4 + threadIdx.x] = 0.f;
+    } else {
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
+    }
+  }
+}
+
+int launch_zero3(pmx_ctx* ctx, cudaStream_t st, float* p0, size_t n0, float* p1, size_t n1, float* p2, size_t n2,
+                 const int* done) {
+  ZeroArgs a;
+  a.p[0] = p0; a.n[0] = n0; a.p[1] = p1; a.n[1] = n1; a.p[2] = p2; a.n[2] = n2;
+  size_t nmax = n0 > n1 ? n0 : n1;
+  if (n2 > nmax) nmax = n2;
+  if (nmax == 0) return PMX_OK;
+  long long blocks = (long long)((nmax / 4 + kThreads - 1) / kThreads);
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_zero3<<<(int)blocks, kThreads, 0, st>>>(a, done);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_zero3");
 }
 
 int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done) {

@@ -393,7 +393,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
   } else if (warp == 2) {
     // ============================== MMA issuer 2: G_A GEMM (after the TMEM allocation above) ================
     // G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (K = n: 8 k-steps).  R (bf16 hi/lo)
-    // sits in the columns of the residual accumulator it was computed from: chunk q = [hi 16 cols | lo 16 cols]
+    // sits in the columns of the residual accumulator it was computed from: every 16 accumulator columns become
+    // [hi 8 cols | lo 8 cols] of packed bf16 pairs
     constexpr uint32_t ID_GA2 = make_idesc(128, 128, 0, 0);   // R_hi from TMEM x [S_hi;S_lo] K-major, N = 128
     constexpr uint32_t ID_GA1 = make_idesc(128, 64, 0, 0);    // R_lo from TMEM x S_hi, N = 64
     uint32_t t = 0, seg = 0;
@@ -411,14 +412,14 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         if (p.ablate & 2) continue;
-        const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8;
+        const uint32_t at = racc + ks * 16;        // R_hi pairs of the 16 columns of k-step ks
         const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);   // K-major, 128 rows
         umma_ts_e(d, at, bd, ID_GA2, (!first || ks) ? 1u : 0u);
       }
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         if (p.ablate & 2) continue;
-        const uint32_t at = racc + (ks >> 1) * 32 + (ks & 1) * 8 + 16;
+        const uint32_t at = racc + ks * 16 + 8;    // R_lo pairs
         const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);   // K-major, rows 0..63
         umma_ts_e(d, at, bd, ID_GA1, 1u);
       }
@@ -495,7 +496,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(bar(B_Y_EMPTY + q));   // the Y values are in registers: refill the slot now
         tmem_ld_wait();
         const float* yf = reinterpret_cast<const float*>(yv);
-        uint32_t hl[32];   // [0,16) = hi pairs, [16,32) = lo pairs
+        uint32_t hl[32];   // per 16 columns: [hi 8 pairs | lo 8 pairs]
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float r0 = __uint_as_float(acc[j]) - yf[j];          // nmf.py:40  (A S - Y)
@@ -507,8 +508,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
           const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);
           const float2 hf = __bfloat1622float2(h);
           const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - hf.x, r1 - hf.y);
-          hl[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          hl[16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l);
+          hl[(j >> 4) * 16 + ((j >> 1) & 7)] = *reinterpret_cast<const uint32_t*>(&h);
+          hl[(j >> 4) * 16 + 8 + ((j >> 1) & 7)] = *reinterpret_cast<const uint32_t*>(&l);
         }
         tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32, hl);
         tmem_st16(lane_addr + TM_ACC + slot * 128 + q * 32 + 16, hl + 16);
@@ -524,7 +525,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
         const int q = qq * 2 + grp;
-        uint32_t hl[32];
+        uint32_t hl[32];   // per 16 columns: [hi 8 | lo 8] pairs
         tmem_ld32(lane_addr + TM_ACC + slot * 128 + q * 32, hl);
         tmem_ld_wait();
         uint8_t* rh = base_ptr + OFF_R_HI + (q >> 1) * PANEL_R + row * 128;
@@ -533,9 +534,9 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         for (int c = 0; c < 4; ++c) {
           if (p.ablate & 16) continue;
           const int chunk = ((q & 1) * 4 + c) ^ (row & 7);
-          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hl[4 * c], hl[4 * c + 1], hl[4 * c + 2], hl[4 * c + 3]);
-          *reinterpret_cast<uint4*>(rl + (chunk << 4)) =
-              make_uint4(hl[16 + 4 * c], hl[16 + 4 * c + 1], hl[16 + 4 * c + 2], hl[16 + 4 * c + 3]);
+          const int o = (c >> 1) * 16 + (c & 1) * 4;     // hi pairs of elements 8c .. 8c+7
+          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hl[o], hl[o + 1], hl[o + 2], hl[o + 3]);
+          *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(hl[o + 8], hl[o + 9], hl[o + 10], hl[o + 11]);
         }
       }
       tc_fence_before();
@@ -575,7 +576,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
         if (warp == 12) TR(4, t, 1);
-        if (!(p.ablate & 32)) {
+        if (!(p.ablate & 32) && !((p.ablate & 64) && (t & 1))) {
           if ((p.N & 3) == 0) {
             // 4x4 quad transposes: lane 4j+r ends up with G_S[k = 4i+r][n = 4j .. 4j+3] -> one 16-byte red per
             // 4 values (16 instead of 64 reductions per thread; a warp-level red covers 4 full 128-byte lines)
@@ -711,10 +712,10 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   pl->Mp = pmx_div_up(M, TILE_M) * TILE_M;
   pl->Np = pmx_div_up(N, TILE_N) * TILE_N;
   PMX_CUDA(cudaSetDevice(ctx->device));
-  PMX_CUDA(cudaMalloc(&pl->Ahi, (size_t)pl->Mp * KP * 2));
-  PMX_CUDA(cudaMalloc(&pl->Alo, (size_t)pl->Mp * KP * 2));
-  PMX_CUDA(cudaMalloc(&pl->Shi, (size_t)KP * pl->Np * 2));
-  PMX_CUDA(cudaMalloc(&pl->Slo, (size_t)KP * pl->Np * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Ahi, (size_t)pl->Mp * KP * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Alo, (size_t)pl->Mp * KP * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Shi, (size_t)KP * pl->Np * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Slo, (size_t)KP * pl->Np * 2));
   PMX_CUDA(cudaMemsetAsync(pl->Ahi, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(pl->Alo, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(pl->Shi, 0, (size_t)KP * pl->Np * 2, ctx->stream));
@@ -734,12 +735,12 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   return PMX_OK;
 }
 
-void umma_plan_destroy(UmmaPlan* pl) {
+void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* pl) {
   if (!pl) return;
-  cudaFree(pl->Ahi);
-  cudaFree(pl->Alo);
-  cudaFree(pl->Shi);
-  cudaFree(pl->Slo);
+  pmx_dev_free(ctx, pl->Ahi);
+  pmx_dev_free(ctx, pl->Alo);
+  pmx_dev_free(ctx, pl->Shi);
+  pmx_dev_free(ctx, pl->Slo);
   delete pl;
 }
 
@@ -753,9 +754,8 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
     PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
     PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
   }
-  PMX_CHECK(launch_zero(ctx, ctx->stream, GA, (size_t)pl->M * pl->K, done));
-  PMX_CHECK(launch_zero(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, done));
-  if (loss) PMX_CHECK(launch_zero(ctx, ctx->stream, reinterpret_cast<float*>(loss), 2, done));
+  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, GA, (size_t)pl->M * pl->K,
+                         reinterpret_cast<float*>(loss), loss ? 2 : 0, done));
   Params p;
   p.M = pl->M; p.N = pl->N; p.K = pl->K;
   p.NS = pl->Np / TILE_N;

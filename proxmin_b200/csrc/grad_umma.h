@@ -8,7 +8,7 @@ struct UmmaPlan;
 bool umma_supported(int M, int N, int K);
 // Y must be 16-byte aligned with a row pitch (ldY floats) that is a multiple of 4
 int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out);
-void umma_plan_destroy(UmmaPlan* plan);
+void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // skip_split != 0: the plan's bf16 (hi, lo) operand buffers already hold the split of (A, S) -- the fused update
 // kernels wrote them -- so the two split passes are skipped
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* plan, const float* A, const float* S, float* GA, float* GS, double* loss,

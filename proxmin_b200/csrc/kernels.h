@@ -3,6 +3,8 @@
 #include "prox.cuh"
 
 int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done);
+int launch_zero3(pmx_ctx* ctx, cudaStream_t st, float* p0, size_t n0, float* p1, size_t n1, float* p2, size_t n2,
+                 const int* done);
 int launch_extrapolate(pmx_ctx* ctx, const float* X, const float* Xold, float* Xe, size_t n, float omega,
                        const int* done);
 int launch_split_bf16(pmx_ctx* ctx, const float* X, int rows, int cols, void* hi, void* lo, int rows_pad, int ld_dst,
@@ -18,6 +20,7 @@ int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, cons
 
 // solver_kernels.cu
 int launch_diff_norms(pmx_ctx* ctx, const float* X, const float* Xold, size_t n, double* norms, const int* done);
+int upd_cols_blocks(pmx_ctx* ctx, int cols);   // grid of the column-owner update kernel = fused Gram partials
 int launch_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* out, const int* done);
 int apply_chain_general(pmx_ctx* ctx, const ProxChain& ch, float* X, int rows, int cols, const StepSpec& step,
                         double* sums_scratch, const int* done);

@@ -26,6 +26,8 @@ struct pmx_nmf {
   pmx_ctl* h_ctl;   // pinned host mirror
   UmmaPlan* plan;   // tcgen05 gradient kernel state (tensor maps, bf16 operand buffers); lazily built
   float* gram_part; // per-block partial Gram matrices of S written by the fused S update
+  bool gram_pending; // the fused update left per-block Gram partials of S that still have to be summed into gramS
+  int gram_pending_blocks;
   bool gramS_valid; // gramS already holds S S^T of the current S (fused update): skip the standalone Gram pass
   bool split_valid; // plan's bf16 operand buffers hold the split of the current (A, S) (written by the update kernels)
   bool used_umma;   // the last gradient evaluation went through the tcgen05 kernel
@@ -59,6 +61,7 @@ __global__ void k_pgm_finalize(pmx_ctl* ctl, float e2A, float e2S) {
   ctl->conv[1] = cS;
   ctl->it += 1;
   if (cA && cS) ctl->done = 1;
+  for (int i = 0; i < 8; ++i) ctl->norms[i] = 0.0;   // ready for the next iteration's update kernels
 }
 
 __global__ void k_ctl_clear_norms(pmx_ctl* ctl) {
@@ -66,9 +69,8 @@ __global__ void k_ctl_clear_norms(pmx_ctl* ctl) {
   for (int i = threadIdx.x; i < 8; i += blockDim.x) ctl->norms[i] = 0.0;
 }
 
-int alloc_f(float** p, size_t n) {
-  PMX_CUDA(cudaMalloc((void**)p, sizeof(float) * (n ? n : 1)));
-  return PMX_OK;
+int alloc_f(pmx_ctx* ctx, float** p, size_t n) {
+  return pmx_dev_alloc(ctx, (void**)p, sizeof(float) * (n ? n : 1));
 }
 
 int pull_ctl(pmx_nmf* h) {
@@ -112,7 +114,12 @@ int nmf_steps(pmx_nmf* h, const float* A, const float* S, bool need_A, bool need
   pmx_ctx* ctx = h->ctx;
   PMX_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-  if (need_A && !(h->gramS_valid && S == h->S)) {  // Gram of S: sum over this rank's columns, then over ranks
+  if (need_A && h->gramS_valid && S == h->S && h->gram_pending) {
+    // partial Gram matrices written by the previous S update: summed here, off the main stream's critical path
+    PMX_CHECK(launch_gram_reduce(ctx, ctx->aux, h->gram_part, h->gram_pending_blocks, h->K, h->gramS, &h->ctl->done));
+    if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->aux));
+    h->gram_pending = false;
+  } else if (need_A && !(h->gramS_valid && S == h->S)) {  // Gram of S: sum over this rank's columns, then over ranks
     PMX_CHECK(launch_gram(ctx, ctx->aux, S, h->K, h->N, false, h->gramS, &h->ctl->done));
     if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->aux));
   }
@@ -168,13 +175,13 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   h->N_global = (double)N_local;
   PMX_CUDA(cudaSetDevice(ctx->device));
   const size_t mk = (size_t)M * K, kn = (size_t)K * N_local;
-  PMX_CHECK(alloc_f(&h->Y, (size_t)M * h->ldY));
-  PMX_CHECK(alloc_f(&h->A, mk));
-  PMX_CHECK(alloc_f(&h->S, kn));
-  PMX_CHECK(alloc_f(&h->A_old, mk));
-  PMX_CHECK(alloc_f(&h->S_old, kn));
-  PMX_CHECK(alloc_f(&h->GA, mk));
-  PMX_CHECK(alloc_f(&h->GS, kn));
+  PMX_CHECK(alloc_f(h->ctx, &h->Y, (size_t)M * h->ldY));
+  PMX_CHECK(alloc_f(h->ctx, &h->A, mk));
+  PMX_CHECK(alloc_f(h->ctx, &h->S, kn));
+  PMX_CHECK(alloc_f(h->ctx, &h->A_old, mk));
+  PMX_CHECK(alloc_f(h->ctx, &h->S_old, kn));
+  PMX_CHECK(alloc_f(h->ctx, &h->GA, mk));
+  PMX_CHECK(alloc_f(h->ctx, &h->GS, kn));
   PMX_CUDA(cudaMalloc((void**)&h->gramA, sizeof(double) * K * K));
   PMX_CUDA(cudaMalloc((void**)&h->gramS, sizeof(double) * K * K));
   PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(pmx_ctl)));
@@ -192,15 +199,15 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   cudaStreamSynchronize(h->ctx->aux);
-  if (h->gram_part) cudaFree(h->gram_part);
+  if (h->gram_part) pmx_dev_free(h->ctx, h->gram_part);
   float* bufs[] = {h->Y, h->A, h->S, h->A_old, h->S_old, h->Ae, h->Se, h->GA, h->GS, h->MA, h->MS, h->VA, h->VS,
                    h->VhA, h->VhS, h->Psi, h->Z0, h->Z1, h->alphaA, h->alphaS};
   for (float* b : bufs)
-    if (b) cudaFree(b);
+    if (b) pmx_dev_free(h->ctx, b);
   for (int j = 0; j < 2; ++j)
     for (int i = 0; i < 4; ++i) {
-      if (h->Zg[j][i]) cudaFree(h->Zg[j][i]);
-      if (h->Ug[j][i]) cudaFree(h->Ug[j][i]);
+      if (h->Zg[j][i]) pmx_dev_free(h->ctx, h->Zg[j][i]);
+      if (h->Ug[j][i]) pmx_dev_free(h->ctx, h->Ug[j][i]);
     }
   if (h->bs_norms) cudaFree(h->bs_norms);
   cudaFree(h->gramA);
@@ -208,7 +215,7 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaFree(h->ctl);
   cudaFreeHost(h->h_ctl);
   if (h->pgm_graph) cudaGraphExecDestroy(h->pgm_graph);
-  if (h->plan) umma_plan_destroy(h->plan);
+  if (h->plan) umma_plan_destroy(h->ctx, h->plan);
   delete h;
   return PMX_OK;
 }
@@ -251,6 +258,7 @@ int pmx_nmf_set(pmx_nmf* h, int which, const float* host_src) {
   if (which == PMX_A || which == PMX_S) {
     h->split_valid = false;
     h->gramS_valid = false;
+  h->gram_pending = false;
   }
   return pmx_h2d(h->ctx, p, host_src, n * sizeof(float));
 }
@@ -272,12 +280,12 @@ int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
   PMX_REQUIRE(h && loss_host, "NULL argument");
   // scratch gradients: the loss is a by-product of the residual pass
   float *ga, *gs;
-  PMX_CHECK(alloc_f(&ga, (size_t)h->M * h->K));
-  PMX_CHECK(alloc_f(&gs, (size_t)h->K * h->N));
+  PMX_CHECK(alloc_f(h->ctx, &ga, (size_t)h->M * h->K));
+  PMX_CHECK(alloc_f(h->ctx, &gs, (size_t)h->K * h->N));
   int st = nmf_gradient(h, h->A, h->S, ga, gs, &h->ctl->norms[6], 0, nullptr);
   if (st == PMX_OK) st = pull_ctl(h);
-  cudaFree(ga);
-  cudaFree(gs);
+  pmx_dev_free(h->ctx, ga);
+  pmx_dev_free(h->ctx, gs);
   *loss_host = h->h_ctl->norms[6];
   return st;
 }
@@ -288,6 +296,7 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   h->pgm = *opts;
   h->split_valid = false;
   h->gramS_valid = false;
+  h->gram_pending = false;
   if (h->pgm_graph) {
     cudaGraphExecDestroy(h->pgm_graph);
     h->pgm_graph = nullptr;
@@ -298,8 +307,8 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   h->nest_t = 1.0;  // utils.py:195
   h->it_enqueued = 0;
   if (opts->accelerated) {
-    if (!h->Ae) PMX_CHECK(alloc_f(&h->Ae, (size_t)h->M * h->K));
-    if (!h->Se) PMX_CHECK(alloc_f(&h->Se, (size_t)h->K * h->N));
+    if (!h->Ae) PMX_CHECK(alloc_f(h->ctx, &h->Ae, (size_t)h->M * h->K));
+    if (!h->Se) PMX_CHECK(alloc_f(h->ctx, &h->Se, (size_t)h->K * h->N));
   }
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
   return PMX_OK;
@@ -324,8 +333,7 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
     Ae = h->Ae;
     Se = h->Se;
   }
-  k_ctl_clear_norms<<<1, 32, 0, ctx->stream>>>(h->ctl);
-  PMX_LAUNCHED(ctx);
+  // (the norms were zeroed by pgm_begin / the previous iteration's finalize)
   // steps on the side stream, gradient on the main stream (both read the same point, algorithms.py:105-106)
   PMX_CHECK(nmf_steps(h, Ae, Se, true, true));
   PMX_CHECK(nmf_gradient(h, Ae, Se, h->GA, h->GS, nullptr, h->pgm.kernel, done));
@@ -345,25 +353,34 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   io.Xin = Ae; io.G = h->GA; io.Xprev = h->A; io.Xout = h->A; io.Xold_out = h->A_old;
   io.norms = &h->ctl->norms[0]; io.rows = h->M; io.cols = h->K; io.step.ptr = &h->ctl->step[0];
   io.hi = (unsigned short*)Ahi; io.lo = (unsigned short*)Alo; io.ld_split = 64;
-  PMX_CHECK(launch_update(ctx, IN_PGM, h->chA, io));
+  {  // the two block updates are independent (Jacobi, algorithms.py:105-108): A on the side stream, S on the main one
+    PMX_CUDA(cudaEventRecord(ctx->ev_fork2, ctx->stream));
+    PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->aux;
+    const int st = launch_update(ctx, IN_PGM, h->chA, io);
+    ctx->stream = main_stream;
+    PMX_CHECK(st);
+  }
   io.Xin = Se; io.G = h->GS; io.Xprev = h->S; io.Xout = h->S; io.Xold_out = h->S_old;
   io.norms = &h->ctl->norms[3]; io.rows = h->K; io.cols = h->N; io.step.ptr = &h->ctl->step[1];
   io.hi = (unsigned short*)Shi; io.lo = (unsigned short*)Slo; io.ld_split = ldS;
   // S S^T of the new S as a by-product of the update (column-owner kernel only): the next iteration's step_A
   const bool fuse_gram = !h->pgm.accelerated && h->K <= 64 && chain_unity_axis(h->chS) == 0;
-  const int nblk = pmx_div_up(h->N, 128);
+  const int nblk = upd_cols_blocks(ctx, h->N);
   if (fuse_gram) {
-    if (!h->gram_part) PMX_CHECK(alloc_f(&h->gram_part, (size_t)nblk * h->K * h->K));
+    if (!h->gram_part) PMX_CHECK(alloc_f(h->ctx, &h->gram_part, (size_t)nblk * h->K * h->K));
     io.gram_part = h->gram_part;
   }
   PMX_CHECK(launch_update(ctx, IN_PGM, h->chS, io));
   h->split_valid = fuse_split;
-  if (fuse_gram) PMX_CHECK(launch_gram_reduce(ctx, ctx->stream, h->gram_part, nblk, h->K, h->gramS, done));
-  h->gramS_valid = fuse_gram;
-  if (ctx->world > 1) {
-    PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
-    if (fuse_gram) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, (size_t)h->K * h->K, 1, ctx->stream));
-  }
+  h->gramS_valid = fuse_gram;      // (the partials are summed on the side stream at the start of the next iteration)
+  h->gram_pending = fuse_gram;
+  h->gram_pending_blocks = nblk;
+  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+  // join the A update (side stream)
+  PMX_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux));
+  PMX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
   const float eA = h->pgm.e_rel_A, eS = h->pgm.e_rel_S;
   k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, (float)((double)eA * (double)eA), (float)((double)eS * (double)eS));
   PMX_LAUNCHED(ctx);
@@ -432,6 +449,7 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   h->ada = *opts;
   h->split_valid = false;
   h->gramS_valid = false;
+  h->gram_pending = false;
   h->chA = make_chain(&opts->prox_A);
   h->chS = make_chain(&opts->prox_S);
   const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
@@ -439,18 +457,18 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   float** bufs[] = {&h->MA, &h->VA, &h->MS, &h->VS};
   const size_t sizes[] = {mk, mk, kn, kn};
   for (int i = 0; i < 4; ++i) {
-    if (!*bufs[i]) PMX_CHECK(alloc_f(bufs[i], sizes[i]));
+    if (!*bufs[i]) PMX_CHECK(alloc_f(h->ctx, bufs[i], sizes[i]));
     PMX_CUDA(cudaMemsetAsync(*bufs[i], 0, sizeof(float) * sizes[i], h->ctx->stream));   // algorithms.py:348-355
   }
   if (opts->has_vhat) {
-    if (!h->VhA) PMX_CHECK(alloc_f(&h->VhA, mk));
-    if (!h->VhS) PMX_CHECK(alloc_f(&h->VhS, kn));
+    if (!h->VhA) PMX_CHECK(alloc_f(h->ctx, &h->VhA, mk));
+    if (!h->VhS) PMX_CHECK(alloc_f(h->ctx, &h->VhS, kn));
   }
-  if (!h->Psi) PMX_CHECK(alloc_f(&h->Psi, big));
-  if (!h->Z0) PMX_CHECK(alloc_f(&h->Z0, big));
-  if (!h->Z1) PMX_CHECK(alloc_f(&h->Z1, big));
-  if (!h->alphaA) PMX_CHECK(alloc_f(&h->alphaA, h->K));
-  if (!h->alphaS) PMX_CHECK(alloc_f(&h->alphaS, h->K));
+  if (!h->Psi) PMX_CHECK(alloc_f(h->ctx, &h->Psi, big));
+  if (!h->Z0) PMX_CHECK(alloc_f(h->ctx, &h->Z0, big));
+  if (!h->Z1) PMX_CHECK(alloc_f(h->ctx, &h->Z1, big));
+  if (!h->alphaA) PMX_CHECK(alloc_f(h->ctx, &h->alphaA, h->K));
+  if (!h->alphaS) PMX_CHECK(alloc_f(h->ctx, &h->alphaS, h->K));
   if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
   h->ada_it = 0;
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
@@ -590,6 +608,7 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
   h->bs = *opts;
   h->split_valid = false;
   h->gramS_valid = false;
+  h->gram_pending = false;
   const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
   const size_t big = mk > kn ? mk : kn;
   for (int j = 0; j < 2; ++j) {
@@ -597,13 +616,13 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
     const size_t n = j == 0 ? mk : kn;
     const float* X = j == 0 ? h->A : h->S;
     for (int i = 0; i < ng; ++i) {   // Z_ji = X_j.copy(), U_ji = 0   (algorithms.py:787-790, utils.py:244-254)
-      if (!h->Zg[j][i]) PMX_CHECK(alloc_f(&h->Zg[j][i], n));
-      if (!h->Ug[j][i]) PMX_CHECK(alloc_f(&h->Ug[j][i], n));
+      if (!h->Zg[j][i]) PMX_CHECK(alloc_f(h->ctx, &h->Zg[j][i], n));
+      if (!h->Ug[j][i]) PMX_CHECK(alloc_f(h->ctx, &h->Ug[j][i], n));
       PMX_CUDA(cudaMemcpyAsync(h->Zg[j][i], X, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->ctx->stream));
       PMX_CUDA(cudaMemsetAsync(h->Ug[j][i], 0, sizeof(float) * n, h->ctx->stream));
     }
   }
-  if (!h->Z0) PMX_CHECK(alloc_f(&h->Z0, big));
+  if (!h->Z0) PMX_CHECK(alloc_f(h->ctx, &h->Z0, big));
   if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
   PMX_CUDA(cudaMemsetAsync(h->bs_norms, 0, sizeof(double) * 256, h->ctx->stream));
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
@@ -669,7 +688,7 @@ int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, i
     PMX_CHECK(umma_plan_create(ctx, Y, N, M, N, K, &plan));
     int st = launch_grad_umma(ctx, plan, A, S, G_A, G_S, loss_or_null, nullptr);
     cudaStreamSynchronize(ctx->stream);
-    umma_plan_destroy(plan);
+    umma_plan_destroy(ctx, plan);
     return st;
   }
   return launch_grad_simt(ctx, Y, N, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);

@@ -70,8 +70,14 @@ class Problem(object):
         _ffi.check(_ffi.lib().pmx_nmf_set(self.handle, which, a.ctypes.data_as(C.c_void_p)))
 
     def get(self, which, out=None, dtype=np.float32):
-        buf = np.empty(self._shape(which), np.float32)
-        _ffi.check(_ffi.lib().pmx_nmf_get(self.handle, which, buf.ctypes.data_as(C.c_void_p)))
+        shape = self._shape(which)
+        L = _ffi.lib()
+        if out is not None and isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous \
+                and out.shape == shape:
+            _ffi.check(L.pmx_nmf_get(self.handle, which, out.ctypes.data_as(C.c_void_p)))   # straight into the caller's array
+            return out
+        buf = np.empty(shape, np.float32)
+        _ffi.check(L.pmx_nmf_get(self.handle, which, buf.ctypes.data_as(C.c_void_p)))
         if out is not None:
             out[...] = buf
             return out

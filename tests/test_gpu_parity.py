@@ -300,3 +300,28 @@ def test_multi_gpu_sharded():
            "127.0.0.1", "--master-port", "29533", os.path.join(os.path.dirname(__file__), "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_cached_buffers_are_clean_between_solves():
+    """Solver handles reuse device blocks of destroyed handles (pmx_dev_alloc): a second solve must not see state
+    of the first one, and pmx_ctx_trim must leave the context usable."""
+    from proxmin_b200 import _ffi, workloads
+    from proxmin_b200 import nmf as pnmf
+    import proxmin_b200 as pmx
+
+    def solve(seed):
+        Y, A, S = workloads.cfg2(256, 1024, 16, seed=seed)
+        pnmf.nmf(Y, A, S, prox_A=pmx.prox_plus, prox_S=pmx.prox_unity_plus, max_iter=20, e_rel=0)
+        return A, S
+
+    A1, S1 = solve(3)
+    A2, S2 = solve(4)          # same shapes: takes the cached blocks of the first handle
+    A3, S3 = solve(3)
+    # (the gradient accumulates with floating-point reductions whose order varies: equal to rounding, not bitwise)
+    close = lambda a, b: np.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert close(A1, A3) and close(S1, S3)
+    assert not close(A1, A2)
+    _ffi.context().trim()
+    A4, S4 = solve(3)
+    assert close(A1, A4) and close(S1, S4)
