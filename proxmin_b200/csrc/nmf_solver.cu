@@ -52,8 +52,14 @@ struct pmx_nmf {
 
 namespace {
 
-__global__ void k_pgm_finalize(pmx_ctl* ctl, float e2A, float e2S) {
+__global__ void k_pgm_finalize(pmx_ctl* ctl, double* normsS, float e2A, float e2S) {
   if (ctl->done) return;
+  if (normsS) {   // sharded run: the S-block norms arrived through the packed all-reduce buffer
+    for (int i = 0; i < 3; ++i) {
+      ctl->norms[3 + i] = normsS[i];
+      normsS[i] = 0.0;
+    }
+  }
   // algorithms.py:130-133: l2sq(X - X_) <= e_rel**2 * l2sq(X), evaluated in fp32 like the reference
   const bool cA = (float)ctl->norms[0] <= e2A * (float)ctl->norms[1];
   const bool cS = (float)ctl->norms[3] <= e2S * (float)ctl->norms[4];
@@ -183,7 +189,9 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   PMX_CHECK(alloc_f(h->ctx, &h->GA, mk));
   PMX_CHECK(alloc_f(h->ctx, &h->GS, kn));
   PMX_CUDA(cudaMalloc((void**)&h->gramA, sizeof(double) * K * K));
-  PMX_CUDA(cudaMalloc((void**)&h->gramS, sizeof(double) * K * K));
+  // gramS carries 4 extra doubles: the S-block norms of a sharded PGM iteration travel in the same all-reduce
+  PMX_CUDA(cudaMalloc((void**)&h->gramS, sizeof(double) * (K * K + 4)));
+  PMX_CUDA(cudaMemset(h->gramS, 0, sizeof(double) * (K * K + 4)));
   PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(pmx_ctl)));
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), ctx->stream));
   PMX_CUDA(cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)M * h->ldY, ctx->stream));
@@ -364,6 +372,8 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   }
   io.Xin = Se; io.G = h->GS; io.Xprev = h->S; io.Xout = h->S; io.Xold_out = h->S_old;
   io.norms = &h->ctl->norms[3]; io.rows = h->K; io.cols = h->N; io.step.ptr = &h->ctl->step[1];
+  const bool fuse_gram_pre = !h->pgm.accelerated && h->K <= 64 && chain_unity_axis(h->chS) == 0;
+  if (ctx->world > 1 && fuse_gram_pre) io.norms = h->gramS + (size_t)h->K * h->K;   // packed with the Gram all-reduce
   io.hi = (unsigned short*)Shi; io.lo = (unsigned short*)Slo; io.ld_split = ldS;
   // S S^T of the new S as a by-product of the update (column-owner kernel only): the next iteration's step_A
   const bool fuse_gram = !h->pgm.accelerated && h->K <= 64 && chain_unity_axis(h->chS) == 0;
@@ -374,15 +384,29 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   }
   PMX_CHECK(launch_update(ctx, IN_PGM, h->chS, io));
   h->split_valid = fuse_split;
-  h->gramS_valid = fuse_gram;      // (the partials are summed on the side stream at the start of the next iteration)
-  h->gram_pending = fuse_gram;
+  h->gramS_valid = fuse_gram;
+  h->gram_pending = fuse_gram;     // single GPU: the partials are summed on the side stream at the start of the next iteration
   h->gram_pending_blocks = nblk;
-  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+  double* normsS = nullptr;
+  if (ctx->world > 1) {
+    // sharded: one all-reduce carries [S S^T partial sums | the three S-block norms] (an NCCL kernel on the side
+    // stream would have to wait for an SM next to the persistent gradient kernel anyway)
+    const size_t kk = (size_t)h->K * h->K;
+    if (fuse_gram) {
+      PMX_CHECK(launch_gram_reduce(ctx, ctx->stream, h->gram_part, nblk, h->K, h->gramS, done));
+      h->gram_pending = false;
+      normsS = h->gramS + kk;
+      PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, kk + 3, 1, ctx->stream));
+    } else {
+      PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+    }
+  }
   // join the A update (side stream)
   PMX_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux));
   PMX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
   const float eA = h->pgm.e_rel_A, eS = h->pgm.e_rel_S;
-  k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, (float)((double)eA * (double)eA), (float)((double)eS * (double)eS));
+  k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, normsS, (float)((double)eA * (double)eA),
+                                           (float)((double)eS * (double)eS));
   PMX_LAUNCHED(ctx);
   h->it_enqueued += 1;
   return pmx_check_launch(ctx, "pgm iteration");

@@ -1,8 +1,9 @@
 """Multi-GPU host logic on CPU: world_size-2 gloo run of the column-sharded PGM iteration.
 
 The device loop (nmf_solver.cu: pgm_enqueue_iteration) shards Y and S by columns, replicates A and
-exchanges exactly three things per iteration: sum(G_A partials), sum(S S^T partials) for step_A, and the
-three S-block norms.  This test replays that exchange sequence with gloo all-reduces around the oracle's
+exchanges exactly two messages per iteration: sum(G_A partials) after the gradient, and ONE packed buffer
+[S S^T partials of the new S (step_A of the next iteration) | the S-block norms] after the S update.  This test
+replays that exchange sequence with gloo all-reduces around the oracle's
 NumPy pieces and checks it against the unsharded oracle: it pins the partition (workloads.shard_columns)
 and the list of reduced quantities that the NCCL path relies on."""
 import os
@@ -38,16 +39,19 @@ def _worker(rank, world, port, out):
     Yl, Sl = Y[:, lo:hi].copy(), S[:, lo:hi].copy()
     A = A.copy()
     iters = 25
+    gramS = allreduce(Sl.astype(np.float64).dot(Sl.T))       # before the first iteration: S S^T of the start point
     for it in range(iters):
         R = A.dot(Sl) - Yl                                   # local stripe of the residual
-        GA = allreduce(R.dot(Sl.T)).astype(np.float32)       # exchange 1: G_A partials
+        GA = allreduce(R.dot(Sl.T)).astype(np.float32)       # message 1: G_A partials
         GS = A.T.dot(R)                                      # local
-        gramS = allreduce(Sl.astype(np.float64).dot(Sl.T))   # exchange 2: S S^T partials
         step_A = np.float32(1 / np.linalg.eigvalsh(gramS).max())
         step_S = np.float32(1 / orc.lipschitz(A))
         A_new = orc.prox_plus(A - step_A * GA, step_A)
         S_new = orc.prox_unity_plus(Sl - step_S * GS, step_S)   # column sums are local to a stripe
-        nS = allreduce(np.array([((S_new - Sl) ** 2).sum(), (S_new ** 2).sum()]))   # exchange 3: S norms
+        packed = np.concatenate([S_new.astype(np.float64).dot(S_new.T).ravel(),
+                                 [((S_new - Sl) ** 2).sum(), (S_new ** 2).sum(), (Sl ** 2).sum()]])
+        packed = allreduce(packed)                           # message 2: [S S^T of the new S | S-block norms]
+        gramS, nS = packed[:K * K].reshape(K, K), packed[K * K:]
         A, Sl = A_new, S_new
     if rank == 0:
         np.savez(out, A=A, nS=nS)
