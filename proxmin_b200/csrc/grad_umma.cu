@@ -577,7 +577,50 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
         if (warp == 12) TR(4, t, 1);
         if (!(p.ablate & 32) && !((p.ablate & 64) && (t & 1))) {
-          if ((p.N & 3) == 0) {
+          const int n_tile0 = (int)(g % p.NS) * TILE_N;
+          if (p.K == KP && n_tile0 + TILE_N <= p.N && (p.N & 3) == 0) {
+            // Full tile: 16 4x4 quad transposes done in lock step (all first-round shuffles, then all second-round
+            // shuffles) so that the 64 shuffles pipeline instead of forming 16 dependent chains, then 16-byte
+            // reductions with no per-instruction predicate: lane 4j+r ends up with G_S[k = 4i+r][n = 4j .. 4j+3],
+            // a warp-level red covers 4 full 128-byte lines.
+            const bool b0 = lane & 1, b1 = lane & 2;
+            float xa[16], xb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t* s4 = (i < 8) ? &v[4 * i] : &w[4 * (i - 8)];
+              xa[i] = __uint_as_float(b0 ? s4[0] : s4[1]);
+              xb[i] = __uint_as_float(b0 ? s4[2] : s4[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              xa[i] = __shfl_xor_sync(0xffffffffu, xa[i], 1);
+              xb[i] = __shfl_xor_sync(0xffffffffu, xb[i], 1);
+            }
+            float c0[16], c1[16], c2[16], c3[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t* s4 = (i < 8) ? &v[4 * i] : &w[4 * (i - 8)];
+              c0[i] = b0 ? xa[i] : __uint_as_float(s4[0]);
+              c1[i] = b0 ? __uint_as_float(s4[1]) : xa[i];
+              c2[i] = b0 ? xb[i] : __uint_as_float(s4[2]);
+              c3[i] = b0 ? __uint_as_float(s4[3]) : xb[i];
+              xa[i] = b1 ? c0[i] : c2[i];
+              xb[i] = b1 ? c1[i] : c3[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              xa[i] = __shfl_xor_sync(0xffffffffu, xa[i], 2);
+              xb[i] = __shfl_xor_sync(0xffffffffu, xb[i], 2);
+            }
+            float* dst = p.GS + (size_t)(lane & 3) * p.N + (n_tile0 + q4 * 32 + (lane & ~3));
+            const size_t stride4 = (size_t)4 * p.N;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o0 = b1 ? xa[i] : c0[i], o2 = b1 ? c2[i] : xa[i];
+              const float o1 = b1 ? xb[i] : c1[i], o3 = b1 ? c3[i] : xb[i];
+              red_add_v4(dst + i * stride4, o0, o1, o2, o3);
+            }
+          } else if ((p.N & 3) == 0) {
             // 4x4 quad transposes: lane 4j+r ends up with G_S[k = 4i+r][n = 4j .. 4j+3] -> one 16-byte red per
             // 4 values (16 instead of 64 reductions per thread; a warp-level red covers 4 full 128-byte lines)
             const int nq = (int)(g % p.NS) * TILE_N + q4 * 32 + (lane & ~3);
