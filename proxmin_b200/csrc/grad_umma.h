@@ -6,7 +6,7 @@ struct UmmaPlan;
 
 // shapes the tcgen05 kernel takes: K <= 64 (operands are zero-padded to K = 64), any M, any N
 bool umma_supported(int M, int N, int K);
-// Y must be 16-byte aligned with a row pitch (ldY floats) that is a multiple of 4
+// Y: fp32 with a row pitch of ldY floats (any alignment: the kernel reads it with plain coalesced loads)
 int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out);
 void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // skip_split != 0: the plan's bf16 (hi, lo) operand buffers already hold the split of (A, S) -- the fused update

@@ -701,11 +701,10 @@ int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, i
                  float* G_S, double* loss_or_null, int kernel) {
   PMX_REQUIRE(ctx && Y && A && S && G_A && G_S, "NULL argument");
   PMX_REQUIRE(M > 0 && N > 0 && K > 0, "shape must be positive");
-  bool use_umma = (kernel == 2) || (kernel == 0 && umma_supported(M, N, K) && (N % 4 == 0) &&
-                                    (long long)M * N >= 128LL * 128);
+  bool use_umma = (kernel == 2) || (kernel == 0 && umma_supported(M, N, K) && (long long)M * N >= 128LL * 128);
   if (use_umma) {
-    if (!umma_supported(M, N, K) || (N % 4) != 0) {
-      pmx_set_error("tcgen05 gradient kernel needs K <= 64 and N %% 4 == 0 (M=%d N=%d K=%d)", M, N, K);
+    if (!umma_supported(M, N, K)) {
+      pmx_set_error("tcgen05 gradient kernel needs K <= 64 (M=%d N=%d K=%d)", M, N, K);
       return PMX_ERR_UNSUPPORTED;
     }
     UmmaPlan* plan = nullptr;

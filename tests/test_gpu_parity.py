@@ -224,7 +224,8 @@ def test_sdmm_lasso(product):
 
 
 # ---------------------------------------------------------------- tcgen05 kernel vs the SIMT kernel
-@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 512, 8), (300, 1000, 20), (77, 204, 5), (1024, 2048, 64)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 512, 8), (300, 1000, 20), (77, 204, 5), (1024, 2048, 64), (130, 333, 7),
+                                   (257, 129, 33)])
 def test_tcgen05_gradient_matches_fp64(shape):
     """3xBF16-split tensor-core GEMMs: gradients within 2e-5 (relative Frobenius) of an fp64 evaluation"""
     import ctypes as C
