@@ -53,6 +53,18 @@ struct pmx_ctl {
   float pad[2];
 };
 
+// ---- peer-memory exchange (comm.cu): symmetric device regions mapped into every rank of the box over CUDA IPC
+#define PMX_MAX_WORLD 8
+#define PMX_PEER_SETS 4            // independent flag sets (one per exchange point of an iteration)
+struct pmx_peer_region {
+  void* local;                     // this rank's allocation (cudaMalloc)
+  void* peer[PMX_MAX_WORLD];       // the same region of every rank, peer[rank] == local
+  size_t bytes;
+};
+struct pmx_peer_ptrs {             // by-value kernel argument
+  void* p[PMX_MAX_WORLD];
+};
+
 struct pmx_ctx {
   int device;
   int sm_count;
@@ -62,6 +74,12 @@ struct pmx_ctx {
   long long launches;
   // NCCL (dlopen'ed lazily)
   void* nccl_comm;
+  void* nccl_comm_aux;   // second communicator (ncclCommSplit) for collectives on the side stream
+  // peer-memory exchange: flags[set][rank] written by the peers (st.release.sys), epoch counters local
+  int peer_ok;
+  pmx_peer_region peer_flags;
+  unsigned* peer_epoch;  // [PMX_PEER_SETS] device counters, never reset
+  pmx_peer_region peer_arena;   // symmetric scratch for the one-shot all-reduces (grown collectively)
   int world, rank;
   // optional per-launch timing of the dominant kernel (bench.py roofline leg)
   int profile;                 // 0 off, 1 on

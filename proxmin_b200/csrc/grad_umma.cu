@@ -243,6 +243,8 @@ struct Params {
   const float* Y;         // fp32, row pitch ldY floats
   int ldY;
   float* GA;
+  const unsigned* ga_epoch;   // sharded runs: G_A partials go to buffer parity (*ga_epoch + 1) & 1 of a pair, see comm.cu
+  long long ga_stride;        // elements between the two buffers
   float* GS;
   double* loss;
   const int* done;
@@ -503,6 +505,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const uint64_t pol = ABL(128) ? l2_policy_normal() : l2_policy_evict_first();
     const int K = p.K, N = p.N, M = p.M, ldY = p.ldY;
+    float* const GA = p.ga_epoch ? p.GA + (size_t)((*p.ga_epoch + 1u) & 1u) * p.ga_stride : p.GA;
     // shared-memory destinations of this thread's R^T chunk (row n, 128B-swizzled 16-byte chunks): loop invariant
     uint8_t* const rh = base_ptr + OFF_R_HI + (grp >> 1) * PANEL_R + row * 128;
     uint8_t* const rl = base_ptr + OFF_R_LO + (grp >> 1) * PANEL_R + row * 128;
@@ -581,7 +584,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
       const int m = q.mb * TILE_M + row;
       if (m < M) {
-        float* dst = p.GA + (size_t)m * K + grp * 16;
+        float* dst = GA + (size_t)m * K + grp * 16;
         float s[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) s[k] = __uint_as_float(v[k]) + __uint_as_float(w[k]);
@@ -609,6 +612,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       // read from tensor memory exactly once (TMEM reads run at ~64 B/clk per SM); the shared-memory copy of R^T is
       // written from the same registers.  hl layout per 16 columns: [hi 8 pairs | lo 8 pairs]
       uint32_t hl[32];
+      TilePos nxt = pos;
+      nxt.next(NS);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t acc[16];
@@ -634,8 +639,6 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_RT_FULL + slot));       // MMA2(t) may start
       if (warp == 4) TR(3, t, 1);
-      TilePos nxt = pos;
-      nxt.next(NS);
       // ---- R^T from registers to shared memory (the MN-major operand of the G_A GEMM) once MMA3(t-1) released it
       mbar_wait(bar(B_RS_EMPTY), (t & 1) ^ 1);
       if (warp == 4) TR(3, t, 2);
@@ -656,6 +659,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       if (warp == 4) TR(3, t, 3);
       // the Y loads of the next tile, issued after the hand-offs above so that load-queue back pressure never delays
       // the MMA issuers: 64 KB per SM in flight while the tensor pipe works on this tile
+      // (re-loading every Y register right after its use, to keep the loads in flight from draining, was measured
+      // 8 % slower: the load issue then sits on the path to the R^T hand-off)
       if (t + 1 < ntiles) issue_y(nxt);
       // ---- gradient flushes, one tile behind so that they never wait for the tensor pipe in steady state
       if (t > 0) {
@@ -786,12 +791,13 @@ void umma_plan_buffers(UmmaPlan* pl, void** Ahi, void** Alo, void** Shi, void** 
 }
 
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done, int skip_split) {
+                     const int* done, int skip_split, const unsigned* ga_epoch, size_t ga_stride) {
   if (!skip_split) {
     PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
     PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
   }
-  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, GA, (size_t)pl->M * pl->K,
+  // (with ga_epoch the G_A pair lives in the peer arena and is cleared by the consumer of the previous epoch)
+  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, GA, ga_epoch ? 0 : (size_t)pl->M * pl->K,
                          reinterpret_cast<float*>(loss), loss ? 2 : 0, done));
   Params p;
   p.M = pl->M; p.N = pl->N; p.K = pl->K;
@@ -799,6 +805,7 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   p.total_tiles = (long long)(pl->Mp / TILE_M) * p.NS;
   p.Y = pl->Y; p.ldY = pl->ldY;
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
+  p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride;
   {
     const char* ab = getenv("PMX_ABLATE");
     p.ablate = ab ? atoi(ab) : 0;

@@ -11,7 +11,9 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
 void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // skip_split != 0: the plan's bf16 (hi, lo) operand buffers already hold the split of (A, S) -- the fused update
 // kernels wrote them -- so the two split passes are skipped
+// ga_epoch != nullptr (sharded runs over peer memory): GA is the base of a pair of buffers ga_stride elements apart
+// and the partials go to buffer (*ga_epoch + 1) & 1, which its consumer cleared (comm.cu)
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* plan, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done, int skip_split = 0);
+                     const int* done, int skip_split = 0, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0);
 // bf16 operand buffers of the plan: A_hi/A_lo are Mp x 64 (row pitch 64), S_hi/S_lo are 64 x Np (row pitch *ldS)
 void umma_plan_buffers(UmmaPlan* plan, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldS);

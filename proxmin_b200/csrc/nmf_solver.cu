@@ -14,6 +14,13 @@
 #include "grad_umma.h"
 
 int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
+bool pmx_comm_has_aux(pmx_ctx* ctx);
+bool pmx_peer_available(pmx_ctx* ctx);
+int pmx_peer_arena(pmx_ctx* ctx, size_t bytes, pmx_peer_region** out);
+int pmx_peer_reset(pmx_ctx* ctx);
+int pmx_peer_signal(pmx_ctx* ctx, int set, cudaStream_t st, const int* done, const double* copy_src,
+                    size_t copy_offset_bytes, size_t n);
+int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done);
 
 struct pmx_nmf {
   pmx_ctx* ctx;
@@ -36,6 +43,8 @@ struct pmx_nmf {
   ProxChain chA, chS;
   double nest_t;
   int it_enqueued;
+  bool peer_mode;              // sharded PGM: exchanges through peer memory instead of NCCL
+  size_t peer_off_gram;        // arena offset of the (Gram(S), norms) pair
   cudaGraphExec_t pgm_graph;   // steady-state iteration captured once, replayed per iteration (no launch gaps)
   long long pgm_graph_launches; // kernels inside the graph (for the launch counter)
   // ---- adaprox
@@ -88,8 +97,10 @@ int pull_ctl(pmx_nmf* h) {
 }  // namespace
 
 // gradient at (A, S) into (GA, GS) [+ loss], kernel selection, multi-GPU sum of the G_A partials
+// defer_reduce: the caller sums the G_A partials over the ranks itself (PGM does it on the side stream)
+// ga_epoch: peer-memory mode of the tcgen05 kernel (GA = base of the buffer pair in the arena, no reduction here)
 int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* GS, double* loss, int kernel,
-                 const int* done) {
+                 const int* done, bool defer_reduce = false, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0) {
   pmx_ctx* ctx = h->ctx;
   bool use_umma = false;
   if (kernel == 2) use_umma = true;
@@ -101,17 +112,21 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
     }
     if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
     const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
-    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip));
+    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride));
     h->used_umma = true;
   } else {
     h->used_umma = false;
     PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, A, S, h->M, h->N, h->K, GA, GS, loss, done));
   }
   if (ctx->world > 1) {
-    PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
+    if (!defer_reduce) PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
     if (loss) PMX_CHECK(pmx_comm_allreduce_internal(ctx, loss, 1, 1, ctx->stream));
   }
   return PMX_OK;
+}
+
+static bool nmf_uses_umma(pmx_nmf* h, int kernel) {
+  return kernel == 2 || (kernel == 0 && umma_supported(h->M, h->N, h->K) && (long long)h->M * h->N >= 128LL * 128);
 }
 
 // lip/step of both blocks at (A, S): step[0] = 1/lambda_max(S S^T), step[1] = 1/lambda_max(A^T A)
@@ -298,6 +313,38 @@ int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
   return st;
 }
 
+// debug (env PMX_STAGE_TIMES): CUDA-event timeline of one PGM iteration, averaged and printed every 50 iterations
+struct StageTimer {
+  bool on;
+  cudaEvent_t ev[10];
+  double acc[10];
+  int n;
+  StageTimer() : on(getenv("PMX_STAGE_TIMES") != nullptr), n(0) {
+    for (int i = 0; i < 10; ++i) { ev[i] = nullptr; acc[i] = 0; }
+  }
+  void mark(int i, cudaStream_t st) {
+    if (!on) return;
+    if (!ev[i]) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[i], st);
+  }
+  void finish(pmx_ctx* ctx) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux);
+    static const char* names[10] = {"start", "aux:steps done", "zero+grad done", "join steps", "aux:AR(G_A)+A update done",
+                                    "S update done", "gram reduce + AR2 done", "finalize done", "", ""};
+    for (int i = 1; i < 8; ++i) {
+      float ms = 0;
+      if (ev[i] && cudaEventElapsedTime(&ms, ev[0], ev[i]) == cudaSuccess) acc[i] += ms;
+    }
+    if (++n % 50 == 0) {
+      for (int i = 1; i < 8; ++i) printf("STAGE %-28s at %8.1f us\n", names[i], 1e3 * acc[i] / 50), acc[i] = 0;
+      fflush(stdout);
+    }
+  }
+};
+static StageTimer g_stage;
+
 // ------------------------------------------------------------------ PGM
 int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
@@ -319,6 +366,18 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
     if (!h->Se) PMX_CHECK(alloc_f(h->ctx, &h->Se, (size_t)h->K * h->N));
   }
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  // sharded run over peer memory (comm.cu): [G_A partials x 2 | (Gram(S) partial, 3 norms, pad) x 2] in the arena
+  h->peer_mode = false;
+  if (pmx_peer_available(h->ctx) && nmf_uses_umma(h, h->pgm.kernel) && umma_supported(h->M, h->N, h->K) &&
+      !getenv("PMX_NO_PEER_PGM")) {
+    const size_t mk = (size_t)h->M * h->K, kk4 = (size_t)h->K * h->K + 4;
+    h->peer_off_gram = (2 * mk * sizeof(float) + 255) & ~(size_t)255;
+    pmx_peer_region* ar = nullptr;
+    if (pmx_peer_arena(h->ctx, h->peer_off_gram + 2 * kk4 * sizeof(double), &ar) == PMX_OK) {
+      PMX_CHECK(pmx_peer_reset(h->ctx));
+      h->peer_mode = true;
+    }
+  }
   return PMX_OK;
 }
 
@@ -341,11 +400,24 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
     Ae = h->Ae;
     Se = h->Se;
   }
+  g_stage.mark(0, ctx->stream);
   // (the norms were zeroed by pgm_begin / the previous iteration's finalize)
   // steps on the side stream, gradient on the main stream (both read the same point, algorithms.py:105-106)
   PMX_CHECK(nmf_steps(h, Ae, Se, true, true));
-  PMX_CHECK(nmf_gradient(h, Ae, Se, h->GA, h->GS, nullptr, h->pgm.kernel, done));
+  // sharded: the sum of the G_A partials runs on the side stream next to the S update -- a one-shot sum over peer
+  // memory (comm.cu) or, as the fallback, an NCCL all-reduce on its own communicator
+  const bool peer = h->peer_mode && ctx->world > 1;
+  const bool ga_on_aux = peer || pmx_comm_has_aux(ctx);
+  if (peer) {
+    PMX_CHECK(nmf_gradient(h, Ae, Se, static_cast<float*>(ctx->peer_arena.local), h->GS, nullptr, h->pgm.kernel, done,
+                           true, ctx->peer_epoch + 0, mk));
+    PMX_CHECK(pmx_peer_signal(ctx, 0, ctx->stream, done, nullptr, 0, 0));
+  } else {
+    PMX_CHECK(nmf_gradient(h, Ae, Se, h->GA, h->GS, nullptr, h->pgm.kernel, done, ga_on_aux));
+  }
+  g_stage.mark(2, ctx->stream);
   PMX_CHECK(nmf_steps_join(h));
+  g_stage.mark(3, ctx->stream);
   // X[j][:] = prox[j](_X[j] - S[j]*G[j], S[j])   (algorithms.py:107-108) + norms (:130-133) + X_ copy (:102)
   UpdIO io;
   memset(&io, 0, sizeof(io));
@@ -364,11 +436,14 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   {  // the two block updates are independent (Jacobi, algorithms.py:105-108): A on the side stream, S on the main one
     PMX_CUDA(cudaEventRecord(ctx->ev_fork2, ctx->stream));
     PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
+    if (peer) PMX_CHECK(pmx_peer_sum(ctx, 0, 0, mk, h->GA, 0, ctx->aux, done));
+    else if (ga_on_aux) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->GA, mk, 0, ctx->aux));
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->aux;
     const int st = launch_update(ctx, IN_PGM, h->chA, io);
     ctx->stream = main_stream;
     PMX_CHECK(st);
+    g_stage.mark(4, ctx->aux);
   }
   io.Xin = Se; io.G = h->GS; io.Xprev = h->S; io.Xout = h->S; io.Xold_out = h->S_old;
   io.norms = &h->ctl->norms[3]; io.rows = h->K; io.cols = h->N; io.step.ptr = &h->ctl->step[1];
@@ -383,6 +458,7 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
     io.gram_part = h->gram_part;
   }
   PMX_CHECK(launch_update(ctx, IN_PGM, h->chS, io));
+  g_stage.mark(5, ctx->stream);
   h->split_valid = fuse_split;
   h->gramS_valid = fuse_gram;
   h->gram_pending = fuse_gram;     // single GPU: the partials are summed on the side stream at the start of the next iteration
@@ -396,11 +472,17 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
       PMX_CHECK(launch_gram_reduce(ctx, ctx->stream, h->gram_part, nblk, h->K, h->gramS, done));
       h->gram_pending = false;
       normsS = h->gramS + kk;
-      PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, kk + 3, 1, ctx->stream));
+      if (peer) {
+        PMX_CHECK(pmx_peer_signal(ctx, 1, ctx->stream, done, h->gramS, h->peer_off_gram, kk + 4));
+        PMX_CHECK(pmx_peer_sum(ctx, 1, h->peer_off_gram, kk + 4, h->gramS, 1, ctx->stream, done));
+      } else {
+        PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, kk + 3, 1, ctx->stream));
+      }
     } else {
       PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
     }
   }
+  g_stage.mark(6, ctx->stream);
   // join the A update (side stream)
   PMX_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux));
   PMX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
@@ -408,6 +490,8 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   k_pgm_finalize<<<1, 1, 0, ctx->stream>>>(h->ctl, normsS, (float)((double)eA * (double)eA),
                                            (float)((double)eS * (double)eS));
   PMX_LAUNCHED(ctx);
+  g_stage.mark(7, ctx->stream);
+  g_stage.finish(ctx);
   h->it_enqueued += 1;
   return pmx_check_launch(ctx, "pgm iteration");
 }
@@ -422,7 +506,7 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
   for (int i = 0; i < n_iter && !stopped; ++i) {
     // Steady state (tcgen05 kernel, operands split by the update kernels, no extrapolation, no per-launch
     // profiling): the iteration is a fixed kernel sequence on two streams (+ NCCL) -> replay it as a CUDA graph.
-    const bool steady = !no_graph && !h->ctx->profile && !h->pgm.accelerated && h->split_valid && h->used_umma &&
+    const bool steady = !no_graph && !g_stage.on && !h->ctx->profile && !h->pgm.accelerated && h->split_valid && h->used_umma &&
                         h->it_enqueued >= 2;
     if (steady) {
       if (!h->pgm_graph) {
