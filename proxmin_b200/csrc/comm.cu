@@ -157,12 +157,21 @@ __global__ void k_peer_sum(pmx_peer_ptrs parts, size_t offset_bytes, size_t n, T
   if (sizeof(T) == 4 && (n & 3) == 0) {
     const size_t n4 = n >> 2;
     for (size_t i = i0; i < n4; i += step) {
+      // all remote loads first (one NVLink round trip instead of `world` dependent ones), then the sum in rank order
+      float4 v[PMX_MAX_WORLD];
+#pragma unroll
+      for (int r = 0; r < PMX_MAX_WORLD; ++r) {
+        if (r < world) {
+          const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(parts.p[r]) + offset_bytes + par * stride) + i;
+          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w) : "l"(src));
+        }
+      }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < world; ++r) {
-        const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(parts.p[r]) + offset_bytes + par * stride) + i;
-        float4 v;
-        asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+      for (int r = 0; r < PMX_MAX_WORLD; ++r) {
+        if (r < world) {
+          acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w;
+        }
       }
       reinterpret_cast<float4*>(dst)[i] = acc;
       reinterpret_cast<float4*>(static_cast<char*>(parts.p[rank]) + offset_bytes + (par ^ 1) * stride)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,7 +324,7 @@ int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst
   const unsigned* my_flags = reinterpret_cast<const unsigned*>(ctx->peer_flags.local);
   const size_t work = kind == 0 && (n & 3) == 0 ? n / 4 : n;
   int blocks = (int)((work + 255) / 256);
-  if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
+  if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
   if (blocks < 1) blocks = 1;
   if (kind == 0)
     k_peer_sum<float><<<blocks, 256, 0, st>>>(parts, offset_bytes, n, (float*)dst, ctx->peer_epoch, my_flags, set, ctx->world, ctx->rank, done);
