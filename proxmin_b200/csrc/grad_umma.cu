@@ -523,7 +523,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         uint32_t lo = (uint32_t)a0;
         const uint32_t hi = (uint32_t)(a0 >> 32);
         const bool interior = (m0 + 32 <= M) && (n0 + TILE_N <= N);
-        if (interior && __all_sync(0xffffffffu, lo <= 0xffffffffu - 32u * pitch)) {
+        if (interior && pitch <= (1u << 26) && __all_sync(0xffffffffu, lo <= 0xffffffffu - 32u * pitch)) {
           // for a fixed j the 32 lanes read one 128-byte line; one IADD + one LDG per element
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -559,7 +559,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       const uint64_t a0 = reinterpret_cast<uint64_t>(dst);
       uint32_t lo = (uint32_t)a0;
       const uint32_t hi = (uint32_t)(a0 >> 32);
-      if (K == KP && (q.st + 1) * TILE_N <= N && __all_sync(0xffffffffu, lo <= 0xffffffffu - 16u * pitch)) {
+      if (K == KP && (q.st + 1) * TILE_N <= N && pitch <= (1u << 26) && __all_sync(0xffffffffu, lo <= 0xffffffffu - 16u * pitch)) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           red_add_f32_lohi(lo, hi, __uint_as_float(v[k]));
