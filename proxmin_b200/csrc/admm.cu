@@ -9,6 +9,7 @@
 // The arithmetic uses explicit round-to-nearest intrinsics in the reference's operation order (no FMA
 // contraction), so X, Z, U are bit-identical to NumPy's fp32 results.
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -41,51 +42,45 @@ struct PassArgs {
   float* part;        // [gridDim.x][MAXG * 5] per-block partial norms (summed by k_admm_finalize: no same-address atomics)
 };
 
+// NG = number of constraints (compile time: the accumulators and the Z/U registers of unused slots would cost
+// half of the occupancy)
+template <int NG>
 __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
   admm_ctl* ctl = a.ctl;
   if (ctl->done) return;
   const bool reinit = ctl->reinit != 0;   // utils.py:244-254 folded into the pass: Z = X, U = 0
   // scalar recipe in double, then one rounding to fp32 (NumPy weak-scalar promotion of Python floats)
   const double sf_d = a.use_slack ? (double)ctl->slack * a.step_base : a.step_base;   // algorithms.py:482
-  const double sg_d = sf_d * 1 * 1 * (a.n_g > 1 ? a.n_g : 1);                         // utils.py:279
+  const double sg_d = sf_d * 1 * 1 * (NG > 1 ? NG : 1);                         // utils.py:279
   const float sf = (float)sf_d;
   const float sg = (float)sg_d;
   const float ratio = (float)(sf_d / sg_d);     // step_f / step_g   (utils.py:316,333)
   const float cS = (float)(-1.0 / sg_d);        // -1 / step_g       (utils.py:300)
-  float acc[MAXG][5];
+  float acc[NG][5];
 #pragma unroll
-  for (int i = 0; i < MAXG; ++i)
+  for (int i = 0; i < NG; ++i)
 #pragma unroll
     for (int q = 0; q < 5; ++q) acc[i][q] = 0.f;
   int ch_x = 0, ch_r = 0;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n; idx += (size_t)gridDim.x * blockDim.x) {
-    const float x = a.X[idx];
-    float z[MAXG], u[MAXG];
-#pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < a.n_g) {
-        z[i] = reinit ? x : a.Z[i][idx];
-        u[i] = reinit ? 0.f : a.U[i][idx];
-      }
+  // one element of the pass: (x, b, z_i, u_i) -> (x', z_i', u_i'), norms and change flags accumulated
+  auto element = [&](float x, float bv, float (&z)[NG], float (&u)[NG], float& xn_out) {
     // dX = sum_i step_f/step_g_i (X - Z_i + U_i)    (left-to-right like np.sum over the list, utils.py:331-337)
     float dX = __fmul_rn(ratio, __fadd_rn(__fsub_rn(x, z[0]), u[0]));
 #pragma unroll
-    for (int i = 1; i < MAXG; ++i)
-      if (i < a.n_g) dX = __fadd_rn(dX, __fmul_rn(ratio, __fadd_rn(__fsub_rn(x, z[i]), u[i])));
+    for (int i = 1; i < NG; ++i)
+      dX = __fadd_rn(dX, __fmul_rn(ratio, __fadd_rn(__fsub_rn(x, z[i]), u[i])));
     const float xa = __fsub_rn(x, dX);
     // prox_f(Xa, step_f) = Xa - step_f (Xa - b)       (utils.LeastSquaresProx, README.md:82-84)
-    const float xn = __fsub_rn(xa, __fmul_rn(sf, __fsub_rn(xa, a.b[idx])));
-    a.X[idx] = xn;
+    const float xn = __fsub_rn(xa, __fmul_rn(sf, __fsub_rn(xa, bv)));
+    xn_out = xn;
     ch_x |= (xn != x) && !(xn != xn && x != x);
 #pragma unroll
-    for (int i = 0; i < MAXG; ++i)
-      if (i < a.n_g) {
+    for (int i = 0; i < NG; ++i)
+      {
         const float zn = chain_segment(a.chain[i], 0, a.chain[i].n, __fadd_rn(xn, u[i]), sg);  // utils.py:297
         const float r = __fsub_rn(xn, zn);                                                      // utils.py:299
-        const float s = __fmul_rn(cS, __fsub_rn(zn, z[i]));                                     // utils.py:300
+        const float sv = __fmul_rn(cS, __fsub_rn(zn, z[i]));                                    // utils.py:300
         const float un = __fadd_rn(u[i], r);                                                    // utils.py:303
-        a.Z[i][idx] = zn;
-        a.U[i][idx] = un;
         const float r_prev = __fsub_rn(x, z[i]);  // the R of the previous pass (same fp32 subtraction)
         ch_r |= (r != r_prev);
         const float uq = a.dual_uses_step_g ? __fdiv_rn(un, sg) : un;                           // utils.py:359-362
@@ -93,17 +88,81 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
         acc[i][1] = fmaf(zn, zn, acc[i][1]);
         acc[i][2] = fmaf(uq, uq, acc[i][2]);
         acc[i][3] = fmaf(r, r, acc[i][3]);
-        acc[i][4] = fmaf(s, s, acc[i][4]);
+        acc[i][4] = fmaf(sv, sv, acc[i][4]);
+        z[i] = zn;
+        u[i] = un;
       }
+  };
+  // main part: 16-byte accesses, every load of a group issued before the arithmetic (the pass is a pure HBM
+  // stream: 7 arrays for one constraint); the buffers come from cudaMalloc, i.e. are 16-byte aligned
+  const size_t n4 = a.n >> 2;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
+    const float4 x4 = reinterpret_cast<const float4*>(a.X)[g];
+    const float4 b4 = reinterpret_cast<const float4*>(a.b)[g];
+    float4 z4[NG], u4[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      {
+        z4[i] = reinit ? x4 : reinterpret_cast<const float4*>(a.Z[i])[g];
+        u4[i] = reinit ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.U[i])[g];
+      }
+    float xo[4];
+    const float xi[4] = {x4.x, x4.y, x4.z, x4.w}, bi[4] = {b4.x, b4.y, b4.z, b4.w};
+    float zo[NG][4], uo[NG][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float z[NG], u[NG];
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        {
+          z[i] = reinterpret_cast<const float*>(&z4[i])[c];
+          u[i] = reinterpret_cast<const float*>(&u4[i])[c];
+        }
+      element(xi[c], bi[c], z, u, xo[c]);
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        {
+          zo[i][c] = z[i];
+          uo[i][c] = u[i];
+        }
+    }
+    reinterpret_cast<float4*>(a.X)[g] = make_float4(xo[0], xo[1], xo[2], xo[3]);
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      {
+        reinterpret_cast<float4*>(a.Z[i])[g] = make_float4(zo[i][0], zo[i][1], zo[i][2], zo[i][3]);
+        reinterpret_cast<float4*>(a.U[i])[g] = make_float4(uo[i][0], uo[i][1], uo[i][2], uo[i][3]);
+      }
+  }
+  // tail (n not a multiple of 4): scalar, the first threads of block 0
+  if (blockIdx.x == 0) {
+    for (size_t idx = (n4 << 2) + threadIdx.x; idx < a.n; idx += blockDim.x) {
+      const float x = a.X[idx];
+      float z[NG], u[NG];
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        {
+          z[i] = reinit ? x : a.Z[i][idx];
+          u[i] = reinit ? 0.f : a.U[i][idx];
+        }
+      float xn;
+      element(x, a.b[idx], z, u, xn);
+      a.X[idx] = xn;
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        {
+          a.Z[i][idx] = z[i];
+          a.U[i][idx] = u[i];
+        }
+    }
   }
   // block reduction: norms and the two change flags
   __shared__ float red[kT / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < MAXG; ++i)
+  for (int i = 0; i < NG; ++i)
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-      if (i >= a.n_g) continue;   // block-uniform
       float v = acc[i][q];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -199,6 +258,9 @@ struct pmx_admm {
   float* U[MAXG];
   admm_ctl* ctl;
   admm_ctl* h_ctl;
+  cudaGraphExec_t graph;   // one batch of iterations (pass + finalize) captured for pmx_admm_run
+  double graph_step;       // step_f the graph was captured with
+  int graph_len;
 };
 
 static int admm_pull(pmx_admm* h) {
@@ -225,7 +287,12 @@ static int admm_enqueue(pmx_admm* h, double step_base, int use_slack, int manage
   a.dual_uses_step_g = h->opts.dual_uses_step_g;
   a.ctl = h->ctl;
   a.part = h->part;
-  k_admm_pass<<<h->nblocks, kT, 0, ctx->stream>>>(a);
+  switch (h->opts.n_g) {
+    case 1: k_admm_pass<1><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
+    case 2: k_admm_pass<2><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
+    case 3: k_admm_pass<3><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
+    default: k_admm_pass<4><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
+  }
   PMX_LAUNCHED(ctx);
   k_admm_finalize<<<1, 256, 0, ctx->stream>>>(h->ctl, h->opts.n_g, (double)h->n, h->opts.e_rel, h->opts.e_abs, manage,
                                               h->part, h->nblocks);
@@ -258,8 +325,22 @@ int pmx_admm_create(pmx_ctx* ctx, size_t n, const pmx_admm_opts* opts, pmx_admm*
     PMX_CUDA(cudaMalloc((void**)&h->U[i], bytes));
   }
   {
-    long long blocks = (long long)((n + kT - 1) / kT);
-    const long long cap = (long long)ctx->sm_count * 8;
+    long long blocks = (long long)((n / 4 + kT - 1) / kT);
+    // one full wave of resident blocks (grid-stride loop): a partial second wave leaves SMs half empty for the
+    // second half of an HBM-bound pass
+    int occ = 0;
+    cudaError_t oe = cudaSuccess;
+    switch (opts->n_g) {
+      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_pass<1>, kT, 0); break;
+      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_pass<2>, kT, 0); break;
+      case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_pass<3>, kT, 0); break;
+      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_pass<4>, kT, 0); break;
+    }
+    if (oe != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 4;
+    }
+    const long long cap = (long long)ctx->sm_count * occ;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     h->nblocks = (int)blocks;
@@ -280,6 +361,7 @@ int pmx_admm_destroy(pmx_admm* h) {
     if (h->Z[i]) cudaFree(h->Z[i]);
     if (h->U[i]) cudaFree(h->U[i]);
   }
+  if (h->graph) cudaGraphExecDestroy(h->graph);
   cudaFree(h->part);
   cudaFree(h->ctl);
   cudaFreeHost(h->h_ctl);
@@ -330,10 +412,40 @@ int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, in
   if (max_iter == 0) h->h_ctl->done = 1;
   PMX_CUDA(cudaMemcpyAsync(h->ctl, h->h_ctl, sizeof(admm_ctl), cudaMemcpyHostToDevice, h->ctx->stream));
   PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  // A batch of iterations is replayed as one CUDA graph (every kernel honours ctl->done, so overshooting the stopping
+  // iteration is harmless): the host then launches once per batch instead of twice per iteration.
   const int batch = 16;
+  static const bool no_graph = getenv("PMX_NO_GRAPH") != nullptr;
+  if (!no_graph && (!h->graph || h->graph_step != step_f || h->graph_len != batch)) {
+    if (h->graph) {
+      cudaGraphExecDestroy(h->graph);
+      h->graph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    const long long l0 = h->ctx->launches;
+    PMX_CUDA(cudaStreamBeginCapture(h->ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int st = PMX_OK;
+    for (int i = 0; i < batch && st == PMX_OK; ++i) st = admm_enqueue(h, step_f, 1, 1);
+    cudaError_t ce = cudaStreamEndCapture(h->ctx->stream, &g);
+    h->ctx->launches = l0;   // the capture did not execute anything
+    if (st != PMX_OK) return st;
+    if (ce != cudaSuccess || !g) {
+      pmx_set_error("CUDA graph capture of the ADMM batch failed: %s", cudaGetErrorString(ce));
+      return PMX_ERR_CUDA;
+    }
+    PMX_CUDA(cudaGraphInstantiate(&h->graph, g, nullptr, nullptr, 0));
+    cudaGraphDestroy(g);
+    h->graph_step = step_f;
+    h->graph_len = batch;
+  }
   long long guard = 0;
   while (!h->h_ctl->done) {
-    for (int i = 0; i < batch; ++i) PMX_CHECK(admm_enqueue(h, step_f, 1, 1));
+    if (h->graph && !no_graph) {
+      PMX_CUDA(cudaGraphLaunch(h->graph, h->ctx->stream));
+      h->ctx->launches += 2LL * batch;
+    } else {
+      for (int i = 0; i < batch; ++i) PMX_CHECK(admm_enqueue(h, step_f, 1, 1));
+    }
     PMX_CHECK(admm_pull(h));
     if (++guard > (1LL << 26)) break;
   }
