@@ -197,6 +197,23 @@ def nmf_pgm_accel(api):
 
 
 @case
+def nmf_pgm_backtracking(api):
+    """PGM with the Beck-Teboulle backtracking line search (algorithms.py:110-127) the way examples/unmixing.py
+    drives it: f = log_likelihood at the trial point.  The Lipschitz step of A is tripled by a user step function so
+    that the line search really has to halve T (five halvings in the reference, none with the plain steps; making
+    BOTH steps too long sends the reference into ~120 halvings and an overflow -- not a useful test)."""
+    Y, A, S = workloads.cfg1(96, 200, 6, seed=22)
+
+    def step(*X, it=None):
+        sA, sS = api.nmf.step_pgm(*X)
+        return (3.0 * sA, sS)
+
+    api.pgm([A, S], partial(api.nmf.grad_likelihood, Y=Y), step, prox=[api.prox_plus] * 2,
+            max_iter=40, e_rel=0, backtracking=True, f=partial(api.nmf.log_likelihood, Y=Y))
+    return _pack(api, A, S, {"loss": np.float64(api.nmf.log_likelihood(A, S, Y=Y))})
+
+
+@case
 def nmf_pgm_soft(api):
     """L1-regularised S (prox_soft_plus, relative threshold scales with the Lipschitz step)."""
     Y, A, S = workloads.cfg1(96, 200, 6, seed=12)

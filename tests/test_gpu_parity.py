@@ -112,6 +112,19 @@ def test_nmf_pgm_stopping_iteration(product):
     assert_close(got["S"], want["S"], 2e-4, "S")
 
 
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: the backtracking callback loop "
+                                        "(device reductions, host line search) has not run on a B200 yet")
+def test_nmf_pgm_backtracking(product):
+    """PGM with backtracking (algorithms.py:110-127), f = log_likelihood on the device; the same
+    five halvings of T as the reference, factors within 2e-4"""
+    want = load_golden("nmf_pgm_backtracking")
+    got = cases.nmf_pgm_backtracking(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert_close(got["A"], want["A"], 2e-4, "A")
+    assert_close(got["S"], want["S"], 2e-4, "S")
+    assert abs(float(got["loss"]) - float(want["loss"])) <= 1e-3 * float(want["loss"])
+
+
 def test_oracle_agrees_live(product):
     """same seeded inputs, oracle run live next to the device (not just the stored vectors)"""
     orc = apis.oracle()
