@@ -3,9 +3,11 @@
 The device loop (nmf_solver.cu: pgm_enqueue_iteration) shards Y and S by columns, replicates A and
 exchanges exactly two messages per iteration: sum(G_A partials) after the gradient, and ONE packed buffer
 [S S^T partials of the new S (step_A of the next iteration) | the S-block norms] after the S update.  This test
-replays that exchange sequence with gloo all-reduces around the oracle's
+replays that exchange sequence with gloo collectives around the oracle's
 NumPy pieces and checks it against the unsharded oracle: it pins the partition (workloads.shard_columns)
-and the list of reduced quantities that the NCCL path relies on."""
+and the list of reduced quantities that the device path relies on.  Two spellings of the exchange: an all-reduce
+(the NCCL fallback) and an all-gather followed by a sum in rank order in the working precision -- what the
+peer-memory kernels of comm.cu do -- for which the replicas of A must stay bit-identical on every rank."""
 import os
 import sys
 
@@ -16,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode="allreduce"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -29,6 +31,14 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
     def allreduce(x):
+        if mode == "gather":   # k_peer_sum: every rank reads every partial and adds them in rank order, same dtype
+            x = np.ascontiguousarray(x)
+            parts = [torch.empty_like(torch.from_numpy(x)) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(x))
+            acc = np.zeros_like(x)
+            for p in parts:
+                acc = acc + p.numpy()
+            return acc
         t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
         dist.all_reduce(t)
         return t.numpy()
@@ -56,20 +66,25 @@ def _worker(rank, world, port, out):
     if rank == 0:
         np.savez(out, A=A, nS=nS)
     np.save(out + ".S%d.npy" % rank, Sl)
+    np.save(out + ".A%d.npy" % rank, A)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_column_sharded_pgm_matches_unsharded(tmp_path):
+@pytest.mark.parametrize("mode", ["allreduce", "gather"])
+def test_column_sharded_pgm_matches_unsharded(tmp_path, mode):
     torch = pytest.importorskip("torch")
     import torch.multiprocessing as mp
 
     from oracle import proxmin_oracle as orc
     from proxmin_b200 import workloads
 
-    world, port = 2, 29611 + os.getpid() % 200
+    world, port = 2, 29611 + os.getpid() % 200 + (300 if mode == "gather" else 0)
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, mode), nprocs=world, join=True)
+    replicas = [np.load(out + ".A%d.npy" % r) for r in range(world)]
+    if mode == "gather":   # rank-ordered sums: bit-identical replicas, the property the peer exchange guarantees
+        assert all(np.array_equal(replicas[0], a) for a in replicas[1:])
     got = np.load(out)
     S = np.concatenate([np.load(out + ".S%d.npy" % r) for r in range(world)], axis=1)
 
