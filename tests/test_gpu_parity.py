@@ -114,6 +114,7 @@ def test_nmf_pgm_stopping_iteration(product):
 
 @pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: the backtracking callback loop "
                                         "(device reductions, host line search) has not run on a B200 yet")
+@pytest.mark.timeout(120)
 def test_nmf_pgm_backtracking(product):
     """PGM with backtracking (algorithms.py:110-127), f = log_likelihood on the device; the same
     five halvings of T as the reference, factors within 2e-4"""
