@@ -1,59 +1,80 @@
 #!/usr/bin/env python
-"""Benchmark of the proxmin NMF hot path on B200 (BASELINE.json metric and config).
+"""Benchmark of the proxmin hot path on B200 (BASELINE.json metric and configs).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, through the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5]   # this repo (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...            # the reference on the host cores
 
-A "step" is one PGM iteration of ``nmf.nmf`` on config 2 of BASELINE.json: Y = 8192 x 65536, K = 64,
-prox_A = prox_plus, prox_S = prox_unity_plus (algorithms.py:87-135, nmf.py:28-65).  With N GPUs the
-columns of Y and S are split over the ranks (strong scaling: the problem is fixed), A is replicated
-and the G_A partials are summed with one NCCL all-reduce per iteration.
+Default workload = BASELINE config 2: a "step" is one PGM iteration of ``nmf.nmf`` on Y = 8192 x 65536, K = 64,
+prox_A = prox_plus, prox_S = prox_unity_plus (algorithms.py:87-135, nmf.py:28-65).  ``--config 3`` is the same
+shape with the adaprox/AMSGrad backend, ``--config 4`` the ADMM LASSO on 1e7 unknowns, ``--config 5`` the bSDMM
+constrained factorisation Y = 4096 x 131072, K = 128 (one step = one outer iteration = two gradient passes).
+With N GPUs the columns of Y and S are split over the ranks (strong scaling: the problem is fixed and every N
+sees the SAME global Y), A is replicated.
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how every number is obtained.
+Prints ONE JSON line (rank 0).  DESIGN.md section "Measurement" says how every number is obtained.
 """
-import argparse
-import ctypes
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# The reference arm must use every host core even under torchrun, which exports OMP_NUM_THREADS=1 to its workers:
+# the BLAS thread pool is sized when NumPy loads, so this has to happen before the first numpy import.
+if "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
+import argparse  # noqa: E402
+import ctypes  # noqa: E402
+import importlib.util  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+from functools import partial  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from proxmin_b200 import workloads  # noqa: E402
 
-M_FULL, N_FULL, K_FULL = 8192, 65536, 64
-METRIC = "NMF iterations/sec"
 UNIT = "it/s"
+SHAPES = {2: (8192, 65536, 64), 3: (8192, 65536, 64), 5: (4096, 131072, 128)}
+N_ADMM = 10_000_000
+METRICS = {2: "NMF iterations/sec", 3: "NMF iterations/sec", 4: "ADMM iterations/sec", 5: "bSDMM outer iterations/sec"}
 
 
-def workload_name(M, N, K):
-    return "nmf.nmf PGM Y=%dx%d K=%d prox_plus+prox_unity_plus" % (M, N, K)
+def workload_name(cfg, M, N, K):
+    if cfg == 2:
+        return "nmf.nmf PGM Y=%dx%d K=%d prox_plus+prox_unity_plus" % (M, N, K)
+    if cfg == 3:
+        return "nmf.nmf adaprox/AMSGrad Y=%dx%d K=%d prox_plus+prox_plus" % (M, N, K)
+    if cfg == 4:
+        return "admm + prox_soft LASSO n=%d" % N
+    return "nmf.nmf bsdmm CMF Y=%dx%d K=%d proxs_g=[[plus,unity],[plus,soft]]" % (M, N, K)
+
+
+def config_dict(cfg, M, N, K):
+    """identical in both arms (the driver compares them)"""
+    if cfg == 4:
+        return {"workload": workload_name(cfg, M, N, K), "n": N}
+    return {"workload": workload_name(cfg, M, N, K), "M": M, "N": N, "K": K}
+
+
+def algorithmic_bytes(cfg, M, N, K):
+    """SURVEY 8(d) / BASELINE.md section 4, fp32, per step"""
+    if cfg == 2:
+        return 4 * (M * N + 2 * K * N + 2 * M * K)            # read Y once, read+write S, read+write A
+    if cfg == 3:
+        return 4 * (M * N + 2 * K * N + 2 * M * K) + 16 * (K * N + M * K)   # + read/write of the moments M, V
+    if cfg == 4:
+        return 7 * 4 * N                                       # read X,Z,U,b; write X,Z,U
+    return 2 * 4 * M * N + 11 * 4 * (K * N + M * K)            # Y twice; X, 2 Z, 2 U read+write, other factor read
 
 
 def dist_env():
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return world, rank, local
-
-
-def measured_traffic(M, n_loc, K, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_grad_umma launch from the committed ncu capture
-    (profiles/grad_umma_traffic.json); None when the capture is for another shape."""
-    p = os.path.join(ROOT, "profiles", "grad_umma_traffic.json")
-    if not os.path.exists(p):
-        return None
-    t = json.load(open(p))
-    w = t.get("workload", {})
-    if (w.get("M"), w.get("N"), w.get("K")) != (M, n_loc, K):
-        return None
-    return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
 
 
 def init_gloo(world, rank):
@@ -67,26 +88,26 @@ def init_gloo(world, rank):
     return dist
 
 
-def stripe_data(M, N, K, world, rank, seed=1234):
-    """cfg2 recipe.  N>1: every rank draws the same A*, A0 and its own column stripe."""
-    if world == 1:
-        return workloads.cfg2(M, N, K, seed=seed) + ((0, N),)
-    lo, hi = workloads.shard_columns(N, world, rank, align=128)
-    n = hi - lo
-    rng_a = np.random.default_rng(seed)
-    At = rng_a.random((M, K), dtype=np.float32)
-    A0 = rng_a.random((M, K), dtype=np.float32)
-    rng = np.random.default_rng(seed + 1 + rank)
-    St = rng.random((K, n), dtype=np.float32)
-    Y = At @ St
-    sd = np.float32(0.01 * 16.0)  # std(Y) of the recipe is ~16 for K=64 uniform factors; exact value is irrelevant here
-    blk = max(1, (1 << 24) // max(n, 1))
-    for r0 in range(0, M, blk):
-        r1 = min(M, r0 + blk)
-        Y[r0:r1] += sd * rng.standard_normal((r1 - r0, n), dtype=np.float32)
-    np.maximum(Y, 0, out=Y)
-    S0 = rng.random((K, n), dtype=np.float32)
-    return Y, A0, S0, (lo, hi)
+def all_max(dist, values):
+    if dist is None:
+        return list(values)
+    import torch
+
+    t = torch.tensor(list(values), dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def replica_spread(dist, A):
+    """max over elements of (max over ranks - min over ranks) of the replicated factor: 0.0 = replicas identical"""
+    if dist is None:
+        return 0.0
+    import torch
+
+    hi, lo = torch.from_numpy(A.copy()), torch.from_numpy(A.copy())
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return float((hi - lo).abs().max())
 
 
 class ClockSampler(threading.Thread):
@@ -142,63 +163,126 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(M, N, K):
-    # read Y once, read+write S, read+write A, fp32
-    return 4 * (M * N + 2 * K * N + 2 * M * K)
+def measured_traffic(kernel, M, n_loc, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu
+    capture (profiles/*_traffic.json); None when no capture exists for this kernel and shape."""
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if not name.endswith("_traffic.json"):
+            continue
+        t = json.load(open(os.path.join(ROOT, "profiles", name)))
+        w = t.get("workload", {})
+        if t.get("kernel", "k_grad_umma") == kernel and (w.get("M"), w.get("N"), w.get("K")) == (M, n_loc, K):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    return None
 
 
-def oracle_iterations_per_s(Y, A0, S0, iters, warm=1):
-    """The reference algorithm (oracle port, same NumPy calls as nmf.py / algorithms.py) on the host cores."""
+# ------------------------------------------------------------------------------------------------------------
+# CPU side: the reference itself (baseline/_ref, copied from /root/reference by __graft_entry__.build) or, when that
+# copy is absent, the oracle port (identical NumPy call sequence) -- the one place bench.py may execute oracle/
+# ------------------------------------------------------------------------------------------------------------
+def cpu_api():
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "proxmin")
+    if os.path.exists(os.path.join(ref_dir, "__init__.py")):
+        if "proxmin_ref" not in sys.modules:
+            spec = importlib.util.spec_from_file_location("proxmin_ref", os.path.join(ref_dir, "__init__.py"),
+                                                          submodule_search_locations=[ref_dir])
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["proxmin_ref"] = mod
+            spec.loader.exec_module(mod)
+        return "reference", sys.modules["proxmin_ref"]
     from oracle import proxmin_oracle as orc
 
+    return "port", orc
+
+
+def set_blas_threads(n):
+    """size the BLAS pool explicitly (torchrun exports OMP_NUM_THREADS=1); returns the thread count in effect"""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)
+        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    except Exception:
+        return 1
+
+
+def _stamps_to_rate(stamps, warm):
+    dt = np.diff(stamps)[warm:]     # callback k fires at the start of iteration k: differences = whole iterations
+    return len(dt) / float(np.sum(dt))
+
+
+def cpu_steps_per_s(cfg, M, N, K, iters, warm):
+    """Times `iters` steps of config `cfg` on the host cores on a bounded sample; returns (it/s scaled to the full
+    workload, kind, sample description)."""
+    kind, api = cpu_api()
     stamps = []
 
     def cb(*X, it=None):
         stamps.append(time.perf_counter())
 
-    A, S = A0.copy(), S0.copy()
-    orc.nmf(Y, A, S, prox_A=orc.prox_plus, prox_S=orc.prox_unity_plus, algorithm="pgm", max_iter=warm + iters + 1,
-            e_rel=0, callback=cb)
-    # callback k fires at the start of iteration k: differences = whole iterations
-    dt = np.diff(stamps)[warm:]
-    return len(dt) / float(np.sum(dt)), float(np.median(dt))
+    cores = os.cpu_count() or 1
+    if cfg == 4:
+        n = N   # full size: ~0.4 s per iteration, single-threaded NumPy elementwise work
+        b, X = workloads.cfg4(n)
 
+        def prox_f(X, s):
+            return X - s * (X - b)
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
+        def step_f(X, it=None):
+            return 0.5
 
-        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+        api.admm(X, prox_f, step_f, prox_g=partial(api.prox_soft, thresh=0.5), max_iter=warm + iters + 1, e_rel=0,
+                 callback=cb)
+        return _stamps_to_rate(stamps, warm), kind, "full n=%d, %d iterations" % (n, iters)
+    # NMF configs: full M and K, a column sample (cost per step is linear in the number of columns)
+    est_full = {2: 3.1, 3: 4.5, 5: 6.5}[cfg] * 8.0 / max(cores, 1) * (M * N * K) / (8192.0 * 65536 * 64)
+    frac = min(1.0, 45.0 / max((warm + iters + 1) * est_full, 1e-9))
+    Ns = min(N, max(256, int(N * frac) // 128 * 128))
+    if cfg == 5:
+        Y, A, S = workloads.cfg5(M, Ns, K)
+    else:
+        Y, A, S = workloads.cfg2(M, Ns, K, seed=1234)
+    mod = api.nmf if kind == "reference" else api
+    if cfg == 2:
+        mod.nmf(Y, A, S, prox_A=api.prox_plus, prox_S=api.prox_unity_plus, max_iter=warm + iters + 1, e_rel=0,
+                callback=cb)
+    elif cfg == 3:
+        alg = api.adaprox if kind == "reference" else "adaprox"
+        mod.nmf(Y, A, S, algorithm=alg, scheme="amsgrad", max_iter=warm + iters + 1, check_convergence=False,
+                callback=cb)
+    else:
+        alg = api.bsdmm if kind == "reference" else "bsdmm"
+        proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus, partial(api.prox_soft, thresh=0.01)]]
+        mod.nmf(Y, A, S, algorithm=alg, prox_A=api.prox_id, prox_S=api.prox_id, proxs_g=proxs_g,
+                max_iter=warm + iters + 1, e_rel=0, callback=cb)
+    rate = _stamps_to_rate(stamps, warm) * (Ns / float(N))
+    sample = "full M=%d, K=%d, first %d of %d columns, %d steps; it/s scaled by %d/%d (cost linear in N)" % (
+        M, K, Ns, N, iters, Ns, N)
+    return rate, kind, sample
 
 
 def run_reference(args, world, rank):
-    """--impl reference: the reference's CPU algorithm on a bounded column sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (rank 0 only)."""
     if rank != 0:
         return
-    M, N, K = args.M, args.N, args.K
-    total = args.steps + args.warmup + 1
-    # ~3.1 s per full-size fp32 iteration on 8 cores (BASELINE.md); keep the whole run under ~2 minutes
-    est_full = 3.1 * (M * N * K) / (M_FULL * N_FULL * K_FULL)
-    frac = min(1.0, 100.0 / max(total * est_full, 1e-9))
-    Ns = max(128, int(N * frac) // 128 * 128)
-    Ns = min(Ns, N)
-    Y, A0, S0 = workloads.cfg2(M, Ns, K, seed=1234)
-    ips, med = oracle_iterations_per_s(Y, A0, S0, args.steps, warm=args.warmup)
-    value = ips * (Ns / N)  # cost per iteration is linear in the number of columns (O(MNK) + O(MN))
-    cores = blas_threads()
-    sample = "full M=%d, K=%d, first %d of %d columns per step; it/s scaled by %d/%d (cost linear in N)" % (
-        M, K, Ns, N, Ns, N)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    cfg, (M, N, K) = args.config, args.shape
+    cores = set_blas_threads(os.cpu_count() or 1)
+    value, kind, sample = cpu_steps_per_s(cfg, M, N, K, args.steps, args.warmup)
+    if cfg == 4:
+        cores = 1   # NumPy elementwise arithmetic is single-threaded
+    line = {"impl": "reference", "metric": METRICS[cfg], "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(M, N, K), "M": M, "N": N, "K": K},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(cfg, M, N, K),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "host_cpus": os.cpu_count(), "numpy": np.__version__},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------------------
 def pinned_array(shape, dtype=np.float32):
     from proxmin_b200 import _ffi
 
@@ -206,39 +290,86 @@ def pinned_array(shape, dtype=np.float32):
     p = ctypes.c_void_p()
     _ffi.check(_ffi.lib().pmx_host_alloc(n, ctypes.byref(p)))
     buf = (ctypes.c_char * n).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    return arr, p
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
 
-def run_product(args, world, rank, local):
+def setup_product(world, rank, local, comm=True):
+    import proxmin_b200 as pmx
+    from proxmin_b200 import _ffi
+
+    dist = init_gloo(world, rank)
+    os.environ["PROXMIN_B200_DEVICE"] = str(local)
+    ctx = _ffi.context()
+    if world > 1 and comm:
+        box = [ctx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        pmx.init_distributed(box[0], world, rank)
+    return dist, ctx
+
+
+def emit(args, world, cfg, shape, value, ms_step, launches, clocks, e2e, roof, cpu, extra):
+    M, N, K = shape
+    line = {"metric": METRICS[cfg], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(cfg, M, N, K),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_leg(args, world, cfg, shape):
+    if world != 1 or args.no_cpu:
+        return None
+    M, N, K = shape
+    cores = set_blas_threads(os.cpu_count() or 1)
+    value, kind, sample = cpu_steps_per_s(cfg, M, N, K, 3, 1)
+    return {"value": value, "unit": UNIT, "cores": 1 if cfg == 4 else cores, "kind": kind, "sample": sample}
+
+
+def run_nmf(args, world, rank, local):
+    """configs 2, 3, 5: the fused NMF solver loops"""
     import proxmin_b200 as pmx
     from proxmin_b200 import _ffi
     from proxmin_b200 import nmf as pnmf
 
-    M, N, K = args.M, args.N, args.K
-    dist = init_gloo(world, rank)
-    os.environ["PROXMIN_B200_DEVICE"] = str(local)
-    ctx = _ffi.context()
-    if world > 1:
-        box = [ctx.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        pmx.init_distributed(box[0], world, rank)
-
-    Yg, A0, S0, (lo, hi) = stripe_data(M, N, K, world, rank)
+    cfg, (M, N, K) = args.config, args.shape
+    dist, ctx = setup_product(world, rank, local)
+    lo, hi = workloads.shard_columns(N, world, rank, align=128)
     n_loc = hi - lo
-    # host buffers of the public-API (e2e) leg live in pinned memory
-    Y, y_ptr = pinned_array((M, n_loc))
+    if cfg == 5:
+        Yg, A0, S0 = workloads.cfg5_columns(M, N, K, lo, hi)
+    else:
+        Yg, A0, S0 = workloads.cfg2_columns(M, N, K, lo, hi, seed=1234)
+    Y, y_ptr = pinned_array((M, n_loc))     # host buffers of the public-API (e2e) leg live in pinned memory
     Y[...] = Yg
     del Yg
+    plus = [(_ffi.OP_PLUS, 0, 0, 0.0)]
+    unity_plus = plus + [(_ffi.OP_UNITY, 0, 0, 0.0)]
+    check_every = 1 << 30
 
-    chain_A = [(_ffi.OP_PLUS, 0, 0, 0.0)]
-    chain_S = [(_ffi.OP_PLUS, 0, 0, 0.0), (_ffi.OP_UNITY, 0, 0, 0.0)]
+    prob = pnmf.Problem(Y, A0, S0)
+    if cfg == 2:
+        prob.pgm_begin(plus, unity_plus, accelerated=False, e_rel=(0.0, 0.0), kernel=args.kernel, check_every=check_every)
+        run = lambda n: prob.pgm_run(n)[0]                                                       # noqa: E731
+    elif cfg == 3:
+        prob.adaprox_begin(plus, plus, "amsgrad", 0.999, 1e-8, 0.25, (1e-3, 1e-3), False, 1000, kernel=args.kernel)
+        state = {"it": 0}
+        b1 = np.full(args.warmup + 2 * args.steps + 8, 0.9)
+
+        def run(n):
+            i0 = state["it"]
+            state["it"] += n
+            done, _, sub = prob.adaprox_run(n, b1[i0:i0 + n], np.roll(b1, 1)[i0:i0 + n])
+            state["sub"] = sub
+            return done
+    else:
+        gA = [plus, [(_ffi.OP_UNITY, 0, 0, 0.0)]]
+        gS = [plus, [(_ffi.OP_SOFT, 1, 0, 0.01)]]
+        prob.bsdmm_begin([], [], gA, gS, (0.0, 0.0), (0.0, 0.0), kernel=args.kernel)
+        run = lambda n: prob.bsdmm_run(n)[0]                                                     # noqa: E731
 
     # ---------------- device-resident leg: `value` ----------------
-    prob = pnmf.Problem(Y, A0, S0)
-    prob.pgm_begin(chain_A, chain_S, accelerated=False, e_rel=(0.0, 0.0), kernel=args.kernel,
-                   check_every=1 << 30)
-    prob.pgm_run(args.warmup)
+    run(args.warmup)
     ctx.sync()
     if dist is not None:
         dist.barrier()
@@ -249,29 +380,27 @@ def run_product(args, world, rank, local):
     ctx.sync()
     t0 = time.perf_counter()
     ctx.timer_start()
-    done, _, _ = prob.pgm_run(args.steps)
+    done = run(args.steps)
     ms = ctx.timer_stop()
     ctx.sync()
     wall = time.perf_counter() - t0
     launches = ctx.launches() - l0
     assert done == args.steps, "timed region executed %d of %d iterations" % (done, args.steps)
-    # second pass of the same length with per-launch CUDA events around the dominant kernel (on its own stream);
-    # the steady-state CUDA-graph replay is off while events are recorded, so this pass is slightly slower
+    # second pass of the same length with per-launch CUDA events around the dominant kernel (on its own stream); the
+    # steady-state CUDA-graph replay is off while events are recorded, so this pass is slightly slower
     ctx.profile(True)
     ctx.timer_start()
-    done2, _, _ = prob.pgm_run(args.steps)
+    run(args.steps)
     ms_prof = ctx.timer_stop()
     kern_ms, kern_n = ctx.profile_read()
     ctx.profile(False)
     clocks = sampler.summary()
+    ms, wall_ms = all_max(dist, [ms, wall * 1e3])
     if dist is not None:
-        import torch
-
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
         dist.barrier()
-    loss = prob.loss()
+    loss = prob.loss()                      # global (summed over the ranks)
+    A_dev = prob.get(_ffi.A)
+    spread = replica_spread(dist, A_dev)
     prob.close()
     value = args.steps / (ms / 1e3)
 
@@ -280,53 +409,134 @@ def run_product(args, world, rank, local):
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    pnmf.nmf(Y, A_h, S_h, prox_A=pmx.prox_plus, prox_S=pmx.prox_unity_plus, max_iter=args.steps, e_rel=0)
+    if cfg == 2:
+        pnmf.nmf(Y, A_h, S_h, prox_A=pmx.prox_plus, prox_S=pmx.prox_unity_plus, max_iter=args.steps, e_rel=0)
+        d2h = 2 * A0.nbytes + 2 * S0.nbytes     # factors + last gradients handed back (algorithms.py:144)
+    elif cfg == 3:
+        pnmf.nmf(Y, A_h, S_h, algorithm=pmx.adaprox, scheme="amsgrad", max_iter=args.steps, check_convergence=False)
+        d2h = 3 * A0.nbytes + 3 * S0.nbytes     # factors + moments M, V (algorithms.py:423)
+    else:
+        pnmf.nmf(Y, A_h, S_h, algorithm=pmx.bsdmm, prox_A=pmx.prox_id, prox_S=pmx.prox_id,
+                 proxs_g=[[pmx.prox_plus, pmx.prox_unity], [pmx.prox_plus, partial(pmx.prox_soft, thresh=0.01)]],
+                 max_iter=args.steps, e_rel=0)
+        d2h = A0.nbytes + S0.nbytes
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([e2e_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    h2d = (Y.nbytes + A0.nbytes + S0.nbytes) / args.steps
-    d2h = (2 * A0.nbytes + 2 * S0.nbytes) / args.steps  # factors + last gradients handed back (algorithms.py:144)
-    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+    (e2e_s,) = all_max(dist, [e2e_s])
+    h2d = Y.nbytes + A0.nbytes + S0.nbytes
+    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
+           "d2h_bytes_per_step": int(d2h / args.steps),
            "note": "one nmf.nmf() solve of `steps` iterations from pinned host arrays: upload of Y,A,S + loop + "
-                   "download of A,S,G inside the timed region"}
-
+                   "download of the results inside the timed region"}
     if rank != 0:
         return
-    # ---------------- roofline of the dominant kernel ----------------
+    # ---------------- roofline ----------------
     peak, peak_src = measured_peaks()
-    alg = algorithmic_bytes(M, n_loc, K)
+    alg_step = algorithmic_bytes(cfg, M, n_loc, K)
+    roof = None
+    if kern_n > 0:
+        avg_ms = kern_ms / kern_n
+        # one gradient launch streams the Y stripe once: the config-2 figure is the per-launch algorithmic byte count
+        alg_launch = algorithmic_bytes(2, M, n_loc, K)
+        ach = alg_launch / (avg_ms * 1e-3) / 1e9
+        flops = 6.0 * M * n_loc * K
+        step_ach = alg_step / (ms / args.steps * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": measured_traffic("k_grad_umma", M, n_loc, K), "kernel": "k_grad_umma",
+                "avg_launch_ms": avg_ms, "launches_timed": kern_n, "kernel_share_of_step": kern_ms / ms_prof,
+                "peak_source": peak_src,
+                "timing": "per-launch CUDA events in a second pass of `steps` iterations (graph replay off)",
+                "algorithmic_bytes_per_launch": alg_launch, "useful_tflops": flops / (avg_ms * 1e-3) / 1e12,
+                "tensor_tflops_issued_bf16": 3 * flops / (avg_ms * 1e-3) / 1e12,
+                "step": {"algorithmic_bytes_per_step": alg_step, "achieved": step_ach, "frac": step_ach / peak}}
+    cpu = cpu_leg(args, world, cfg, (M, N, K))
+    extra = {"host_wall_ms_per_step": wall_ms / args.steps, "final_loss": loss, "replica_diff": spread,
+             "exchange": "none" if world == 1 else ("peer" if ctx.peer_enabled() else "nccl"),
+             "check_every": check_every,
+             "notes": {"columns_per_gpu": n_loc,
+                       "gemm": "tcgen05 kind::f16, 3-term bf16 split, fp32 accumulate" if args.kernel != 1 else "simt fp32",
+                       "l2": "inputs larger than L2: every step streams the %.2f GB Y stripe" % (M * n_loc * 4 / 1e9)}}
+    if cfg == 3:
+        extra["sub_iterations"] = [int(s) for s in state.get("sub", (0, 0))]
+    emit(args, world, cfg, (M, N, K), value, ms / args.steps, launches, clocks, e2e, roof, cpu, extra)
+
+
+def run_admm(args, world, rank, local):
+    """config 4: ADMM LASSO, fused device loop (one B200; `--gpus N` runs N independent replicas)"""
+    import proxmin_b200 as pmx
+    from proxmin_b200 import _ffi
+
+    cfg, (M, N, K) = 4, args.shape
+    n = N
+    dist, ctx = setup_product(world, rank, local, comm=False)   # independent replicas: no communicator
+    b_h, X0 = workloads.cfg4(n)
+    b, _ = pinned_array((n,))
+    b[...] = b_h
+    L = _ffi.lib()
+    o = _ffi.AdmmOpts()
+    o.n_g = 1
+    o.proxs_g[0] = _ffi.make_prox([(_ffi.OP_SOFT, 1, 0, 0.5)])
+    o.e_rel, o.e_abs, o.dual_uses_step_g = 0.0, 0.0, 0      # e_rel = 0: never converges, fixed iteration count
+    h = ctypes.c_void_p()
+    _ffi.check(L.pmx_admm_create(ctx.handle, n, ctypes.byref(o), ctypes.byref(h)))
+    vp = ctypes.c_void_p
+    it, conv = ctypes.c_int(0), ctypes.c_int(0)
+    err = (ctypes.c_double * 16)()
+    _ffi.check(L.pmx_admm_set(h, X0.ctypes.data_as(vp), b.ctypes.data_as(vp)))
+    _ffi.check(L.pmx_admm_run(h, 0.5, max(args.warmup, 3), ctypes.byref(it), ctypes.byref(conv), err))   # warm-up
+    _ffi.check(L.pmx_admm_set(h, X0.ctypes.data_as(vp), b.ctypes.data_as(vp)))
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(ctx.device)
+    sampler.start()
+    time.sleep(0.05)
+    l0 = ctx.launches()
+    ctx.timer_start()
+    _ffi.check(L.pmx_admm_run(h, 0.5, args.steps, ctypes.byref(it), ctypes.byref(conv), err))
+    ms = ctx.timer_stop()
+    launches = ctx.launches() - l0
+    done = it.value - 1                       # "Completed it + 1 iterations" (algorithms.py:516)
+    assert done == args.steps, (done, args.steps)
+    _ffi.check(L.pmx_admm_set(h, X0.ctypes.data_as(vp), b.ctypes.data_as(vp)))
+    ctx.profile(True)
+    _ffi.check(L.pmx_admm_run(h, 0.5, args.steps, ctypes.byref(it), ctypes.byref(conv), err))
+    kern_ms, kern_n = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.summary()
+    (ms,) = all_max(dist, [ms])
+    _ffi.check(L.pmx_admm_destroy(h))
+    value = world * args.steps / (ms / 1e3)   # N independent replicas (the path does not shard: DESIGN.md section 6)
+    # e2e: the public admm() call on host arrays (upload of X, b; fused loop; download of X)
+    X = X0.copy()
+    t0 = time.perf_counter()
+    pmx.admm(X, pmx.utils.LeastSquaresProx(b), pmx.utils.ConstantStep(0.5), prox_g=partial(pmx.prox_soft, thresh=0.5),
+             max_iter=args.steps, e_rel=0)
+    e2e_s = time.perf_counter() - t0
+    (e2e_s,) = all_max(dist, [e2e_s])
+    e2e = {"value": world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * 4 * n / args.steps),
+           "d2h_bytes_per_step": int(4 * n / args.steps),
+           "note": "one admm() solve of `steps` iterations on host arrays (LeastSquaresProx / ConstantStep / prox_soft): "
+                   "upload of X, b + fused device loop + download of X"}
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(4, 0, n, 0)
     roof = None
     if kern_n > 0:
         avg_ms = kern_ms / kern_n
         ach = alg / (avg_ms * 1e-3) / 1e9
-        flops = 6.0 * M * n_loc * K
+        step_ach = alg / (ms / args.steps * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic(M, n_loc, K, world), "kernel": "k_grad_umma", "avg_launch_ms": avg_ms, "launches_timed": kern_n,
-                "kernel_share_of_step": kern_ms / ms_prof, "peak_source": peak_src,
-                "timing": "per-launch CUDA events in a second pass of `steps` iterations (graph replay off)",
-                "algorithmic_bytes_per_launch": alg, "useful_tflops": flops / (avg_ms * 1e-3) / 1e12,
-                "tensor_tflops_issued_bf16": 3 * flops / (avg_ms * 1e-3) / 1e12}
-    # ---------------- CPU baseline (oracle port) on a bounded sample ----------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        Ns = min(N, max(128, (N // 16) // 128 * 128))
-        Ys, As, Ss = workloads.cfg2(M, Ns, K, seed=1234)
-        ips, med = oracle_iterations_per_s(Ys, As, Ss, 4, warm=1)
-        cpu = {"value": ips * Ns / N, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-               "sample": "4 iterations on the first %d of %d columns (full M, K); it/s scaled by %d/%d" % (Ns, N, Ns, N)}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(M, N, K), "M": M, "N": N, "K": K, "columns_per_gpu": n_loc,
-                       "gemm": "tcgen05 kind::f16, 3-term bf16 split, fp32 accumulate" if args.kernel != 1 else "simt fp32",
-                       "l2": "inputs larger than L2: every iteration streams the %.2f GB Y stripe" % (M * n_loc * 4 / 1e9)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "host_wall_ms_per_step": wall * 1e3 / args.steps, "final_loss": loss}
-    print(json.dumps(line), flush=True)
+                "traffic": measured_traffic("k_admm_pass", 0, n, 0), "kernel": "k_admm_pass", "avg_launch_ms": avg_ms,
+                "launches_timed": kern_n, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "timing": "per-launch CUDA events in a second run of `steps` iterations (graph replay off)",
+                "step": {"algorithmic_bytes_per_step": alg, "achieved": step_ach, "frac": step_ach / peak}}
+    cpu = cpu_leg(args, world, 4, (M, N, K))
+    extra = {"scaling": "weak" if world > 1 else "strong",
+             "notes": {"path": "fused device loop (utils.LeastSquaresProx + utils.ConstantStep + built-in prox_g); a plain "
+                               "Python closure for prox_f takes the callback loop (one host round trip per expression)",
+                       "l2": "X, Z, U, b = 160 MB > L2 (126 MB): every pass streams them from HBM"}}
+    emit(args, world, 4, (M, N, K), value, ms / args.steps, launches, clocks, e2e, roof, cpu, extra)
 
 
 def main():
@@ -335,19 +545,27 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--M", type=int, default=M_FULL)
-    ap.add_argument("--N", type=int, default=N_FULL)
-    ap.add_argument("--K", type=int, default=K_FULL)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (1-based)")
+    ap.add_argument("--M", type=int, default=None)
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--K", type=int, default=None)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
+    if args.config == 4:
+        args.shape = (0, args.N or N_ADMM, 0)
+    else:
+        M0, N0, K0 = SHAPES[args.config]
+        args.shape = (args.M or M0, args.N or N0, args.K or K0)
     world, rank, local = dist_env()
     if args.gpus != world and world == 1 and args.gpus > 1:
         sys.stderr.write("bench.py: --gpus %d needs torchrun (one process per GPU); running 1 GPU\n" % args.gpus)
     if args.impl == "reference":
         run_reference(args, world, rank)
+    elif args.config == 4:
+        run_admm(args, world, rank, local)
     else:
-        run_product(args, world, rank, local)
+        run_nmf(args, world, rank, local)
 
 
 if __name__ == "__main__":

@@ -65,6 +65,8 @@ int pmx_ctx_profile_read(pmx_ctx* ctx, float* total_ms, int* launches);
 int pmx_comm_unique_id(void* unique_id_128);
 int pmx_comm_init(pmx_ctx* ctx, const void* unique_id_128, int world, int rank);
 int pmx_comm_allreduce_sum(pmx_ctx* ctx, float* dev_buf, size_t count);
+/* *enabled = 1 when the ranks of the communicator exchange over CUDA-IPC peer memory (one box), 0 = NCCL only */
+int pmx_comm_peer_enabled(pmx_ctx* ctx, int* enabled);
 
 /* ------------------------------------------------------------------- memory */
 int pmx_malloc(pmx_ctx* ctx, size_t bytes, void** dev_ptr);
@@ -162,7 +164,7 @@ typedef struct {
   pmx_prox prox_A, prox_S;
   int32_t has_prox_A, has_prox_S; /* algorithms.py:380: prox None skips the sub-iterations */
   int32_t scheme;                 /* algorithms.py:338-345 */
-  float b2, eps, p;               /* algorithms.py:255-258 */
+  double b2, eps, p;              /* algorithms.py:255-258 (Python floats in the reference: kept in double) */
   float e_rel_A, e_rel_S;
   int32_t check_convergence;      /* algorithms.py:257,371,403 */
   int32_t prox_max_iter;          /* algorithms.py:261,386 */
@@ -241,7 +243,7 @@ int pmx_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, dou
  * alpha: mode 0 = scalar alpha_value, 2 = per-column vector alpha_dev[cols], 3 = per-row vector alpha_dev[rows]. */
 int pmx_adaprox_moments(pmx_ctx* ctx, int scheme, const float* G, float* M, float* V, float* Vhat_or_null, float* X,
                         float* Psi, int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value,
-                        double b1, double b1_prev, float b2, float eps, float p, int t, float* psimax_host);
+                        double b1, double b1_prev, double b2, double eps, double p, int t, float* psimax_host);
 int pmx_adaprox_sub(pmx_ctx* ctx, const pmx_prox* prox, const float* Z, const float* X, const float* Psi, float* Zout,
                     int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value, float psimax,
                     double* norms_host);

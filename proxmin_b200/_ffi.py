@@ -35,7 +35,7 @@ class PgmOpts(C.Structure):
 
 class AdaproxOpts(C.Structure):
     _fields_ = [("prox_A", Prox), ("prox_S", Prox), ("has_prox_A", C.c_int32), ("has_prox_S", C.c_int32),
-                ("scheme", C.c_int32), ("b2", C.c_float), ("eps", C.c_float), ("p", C.c_float),
+                ("scheme", C.c_int32), ("b2", C.c_double), ("eps", C.c_double), ("p", C.c_double),
                 ("e_rel_A", C.c_float), ("e_rel_S", C.c_float), ("check_convergence", C.c_int32),
                 ("prox_max_iter", C.c_int32), ("has_vhat", C.c_int32), ("kernel", C.c_int32),
                 ("step_mode", C.c_int32), ("alpha_A", C.c_float), ("alpha_S", C.c_float)]
@@ -90,6 +90,7 @@ def _declare(L):
         "pmx_comm_unique_id": [vp],
         "pmx_comm_init": [vp, vp, i32, i32],
         "pmx_comm_allreduce_sum": [vp, vp, sz],
+        "pmx_comm_peer_enabled": [vp, pi],
         "pmx_malloc": [vp, sz, C.POINTER(vp)],
         "pmx_free": [vp, vp],
         "pmx_memset": [vp, vp, i32, sz],
@@ -127,7 +128,7 @@ def _declare(L):
         "pmx_axis_sum": [vp, vp, i32, i32, i32, pd],
         "pmx_ew": [vp, i32, sz, vp, vp, vp, vp, f32, f32, vp, vp, vp, pd],
         "pmx_adaprox_moments": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, f32, C.c_double, C.c_double,
-                                f32, f32, f32, i32, pf],
+                                C.c_double, C.c_double, C.c_double, i32, pf],
         "pmx_adaprox_sub": [vp, C.POINTER(Prox), vp, vp, vp, vp, i32, i32, vp, i32, f32, f32, pd],
     }
     for name, args in sig.items():
@@ -230,6 +231,12 @@ class Context:
         return ms.value
 
     # -- multi-GPU
+    def peer_enabled(self):
+        """True when the sharded solvers exchange over CUDA-IPC peer memory (comm.cu), False = NCCL all-reduces"""
+        v = C.c_int(0)
+        check(lib().pmx_comm_peer_enabled(self.handle, C.byref(v)))
+        return bool(v.value)
+
     def unique_id(self):
         buf = C.create_string_buffer(128)
         check(lib().pmx_comm_unique_id(buf))

@@ -56,17 +56,26 @@ def _is_step(step, fn_name):
     return False
 
 
+def _device_chain(p):
+    """Primitive-op chain of ``p`` if one fused device chain can express it (built-ins only, at most
+    PMX_MAX_OPS primitive ops, prox_unity along a single axis); else None -> the callable runs on the host."""
+    d = operators.describe(p)
+    if d is None or len(d) > _ffi.PMX_MAX_OPS:
+        return None
+    axes = {a for (o, _, a, _) in d if o == _ffi.OP_UNITY}
+    if len(axes) > 1:
+        return None
+    return d
+
+
 def _describe_all(prox, allow_none=False):
     out = []
     for p in prox:
         if p is None and allow_none:
             out.append(None)
             continue
-        d = operators.describe(p)
-        if d is None or len(d) > _ffi.PMX_MAX_OPS:
-            return None
-        axes = {a for (o, _, a, _) in d if o == _ffi.OP_UNITY}
-        if len(axes) > 1:
+        d = _device_chain(p)
+        if d is None:
             return None
         out.append(d)
     return out
@@ -85,10 +94,14 @@ def _writeback(prob, X):
 # ------------------------------------------------------------------------------------------
 # device helpers for the callback loops
 # ------------------------------------------------------------------------------------------
-def _dev_pgm_update(ops, Xe, G, X, step):
-    """X[:] = prox(Xe - step*G) with a built-in chain ``ops``; returns (|X-Xold|^2, |X|^2)."""
+def _dev_pgm_update(ops, Xe, G, X, step, Xold=None):
+    """X[:] = prox(Xe - step*G) with a built-in chain ``ops``; returns (|X-Xold|^2, |X|^2).
+
+    ``Xold`` is the iterate the convergence norms compare against (algorithms.py:130-133: the copy ``X_`` taken
+    before the update); it defaults to the contents of X, which is the same thing except for the re-update of a
+    block inside the backtracking line search (algorithms.py:124), where X already holds the first attempt."""
     ctx = _ffi.context()
-    x32 = np.ascontiguousarray(X, dtype=np.float32)
+    x32 = np.array(X if Xold is None else Xold, dtype=np.float32, order="C", copy=True)
     rows, cols = (1, x32.size) if x32.ndim != 2 else x32.shape
     if x32.ndim != 2:
         ops = [(o, r, 1 if o == _ffi.OP_UNITY else a, t) for (o, r, a, t) in ops]
@@ -197,7 +210,7 @@ def _pgm_callbacks(X, grad, step, prox, accelerated, backtracking, f, e_rel, max
 
     if callback is None:
         callback = utils.NullCallback()
-    chains = [operators.describe(p) for p in prox]
+    chains = [_device_chain(p) for p in prox]
     accel = utils.NesterovAccelerator(accelerated=accelerated)
     T = [1.0] * N
     converged = (False,) * N
@@ -249,7 +262,7 @@ def _update_block(chain, prox, Xe, G, X, Xold, step):
     """One block of algorithms.py:107-108 + the norms of :130-133, forward step on the device."""
     s = _scalar_step(step)
     if chain is not None:
-        return _dev_pgm_update(chain, Xe, G, X, s)
+        return _dev_pgm_update(chain, Xe, G, X, s, Xold=Xold)
     # user prox: forward step on the device, the user's callable on the host, norms on the device
     V = np.array(Xe, dtype=X.dtype, copy=True)
     _dev_pgm_update([], Xe, G, V, s)
@@ -409,7 +422,7 @@ def _adaprox_callbacks(X, grad, step, prox, scheme, b1, b2, eps, check_convergen
     Sub_iter = [0] * N
     if callback is None:
         callback = utils.NullCallback()
-    chains = [operators.describe(pj) if pj is not None else None for pj in prox]
+    chains = [_device_chain(pj) if pj is not None else None for pj in prox]
     b1 = np.asarray(b1, dtype=np.float64)
     converged = (False,) * N
     it = -1
@@ -572,7 +585,7 @@ def admm(
 ):
     """Linearised ADMM with one constraint (algorithms.py:426-520).  Returns ``(converged, errors)``."""
     _no_L(L)
-    chain_g = operators.describe(prox_g) if prox_g is not None else None
+    chain_g = _device_chain(prox_g) if prox_g is not None else None
 
     if (prox_g is not None and step_g is None and callback is None
             and _fusable_admm(X, prox_f, step_f, [chain_g])):
@@ -638,7 +651,7 @@ def sdmm(
                     callback=callback)
     _no_L(Ls)
     M = len(proxs_g)
-    chains = [operators.describe(pg) for pg in proxs_g]
+    chains = [_device_chain(pg) for pg in proxs_g]
 
     if steps_g is None and callback is None and _fusable_admm(X, prox_f, step_f, chains):
         converged, _, logged = _admm_device(X, prox_f.b, step_f.value, chains, e_rel, e_abs, max_iter,
@@ -727,7 +740,7 @@ def bsdmm(
             if not hasattr(proxs_g[j], "__iter__"):
                 proxs_g[j] = [proxs_g[j]]
             M[j] = len(proxs_g[j])
-            chains[j] = [operators.describe(pg) for pg in proxs_g[j]]
+            chains[j] = [_device_chain(pg) for pg in proxs_g[j]]
 
     Z, U = [], []
     for j in range(N):

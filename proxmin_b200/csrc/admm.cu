@@ -287,11 +287,17 @@ static int admm_enqueue(pmx_admm* h, double step_base, int use_slack, int manage
   a.dual_uses_step_g = h->opts.dual_uses_step_g;
   a.ctl = h->ctl;
   a.part = h->part;
+  const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;   // per-launch events around the pass (bench.py roofline)
+  if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
   switch (h->opts.n_g) {
     case 1: k_admm_pass<1><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
     case 2: k_admm_pass<2><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
     case 3: k_admm_pass<3><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
     default: k_admm_pass<4><<<h->nblocks, kT, 0, ctx->stream>>>(a); break;
+  }
+  if (prof) {
+    PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream));
+    ctx->prof_n++;
   }
   PMX_LAUNCHED(ctx);
   k_admm_finalize<<<1, 256, 0, ctx->stream>>>(h->ctl, h->opts.n_g, (double)h->n, h->opts.e_rel, h->opts.e_abs, manage,
@@ -415,7 +421,7 @@ int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, in
   // A batch of iterations is replayed as one CUDA graph (every kernel honours ctl->done, so overshooting the stopping
   // iteration is harmless): the host then launches once per batch instead of twice per iteration.
   const int batch = 16;
-  static const bool no_graph = getenv("PMX_NO_GRAPH") != nullptr;
+  const bool no_graph = getenv("PMX_NO_GRAPH") != nullptr || h->ctx->profile;
   if (!no_graph && (!h->graph || h->graph_step != step_f || h->graph_len != batch)) {
     if (h->graph) {
       cudaGraphExecDestroy(h->graph);

@@ -143,6 +143,8 @@ int pmx_ctx_destroy(pmx_ctx* ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->aux);
   cudaFreeHost(ctx->h_flags);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->gram_scratch[i]) cudaFree(ctx->gram_scratch[i]);
   pmx_dev_trim(ctx);
   delete static_cast<DevPool*>(ctx->pool);
   if (ctx->prof_ev) {

@@ -385,6 +385,12 @@ int pmx_comm_init(pmx_ctx* ctx, const void* unique_id_128, int world, int rank) 
   return pmx_peer_setup_internal(ctx);
 }
 
+int pmx_comm_peer_enabled(pmx_ctx* ctx, int* enabled) {
+  PMX_REQUIRE(ctx && enabled, "NULL argument");
+  *enabled = pmx_peer_available(ctx) ? 1 : 0;
+  return PMX_OK;
+}
+
 int pmx_comm_allreduce_sum(pmx_ctx* ctx, float* dev_buf, size_t count) {
   PMX_REQUIRE(ctx && dev_buf, "NULL argument");
   return pmx_comm_allreduce_internal(ctx, dev_buf, count, 0, ctx->stream);

@@ -90,6 +90,9 @@ struct pmx_ctx {
   char dev_name[128];
   size_t total_mem;
   void* pool;            // cache of freed device blocks (pmx_dev_alloc / pmx_dev_free), see api.cu
+  // scratch of launch_gram (per-block partial Gram matrices): one buffer per (tall/wide, main/side stream)
+  float* gram_scratch[4];
+  size_t gram_scratch_bytes[4];
 };
 
 static inline int pmx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

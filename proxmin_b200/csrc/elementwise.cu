@@ -735,8 +735,9 @@ __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
   float pm = 0.f;
   // scalar recipe pieces, evaluated in fp32 like NumPy does for fp32 arrays with Python scalars
   const double c1 = 1.0 - pow(a.b1, (double)a.t);                   // 1 - b1[it]**t  (np.float64 scalar)
-  const float c2 = (float)(1.0 - pow((double)a.b2, (double)a.t));   // 1 - b2**t      (Python float -> weak fp32)
-  const float omb2 = (float)(1.0 - (double)a.b2);
+  const float c2 = (float)(1.0 - pow(a.b2, (double)a.t));   // 1 - b2**t      (Python float -> weak fp32)
+  const float omb2 = (float)(1.0 - a.b2);
+  const float b2f = (float)a.b2, epsf = (float)a.eps, pf = (float)a.p;
   float radam_r = 0.f;
   bool radam_rect = false;
   if (a.scheme == PMX_RADAM) {  // algorithms.py:222-239 (scalar part, double like Python floats)
@@ -755,7 +756,7 @@ __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
     }
     const float g = a.G[i];
     const float m = (float)((1.0 - a.b1) * (double)g + a.b1 * (double)a.M[i]);
-    const float v = omb2 * (g * g) + a.b2 * a.V[i];
+    const float v = omb2 * (g * g) + b2f * a.V[i];
     a.M[i] = m;
     a.V[i] = v;
     double phi;  // Phi is float64 in the reference whenever b1[it] enters it
@@ -763,16 +764,16 @@ __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
     switch (a.scheme) {
       case PMX_ADAM:
         phi = (double)m / c1;
-        psi = sqrtf(v / c2) + a.eps;
+        psi = sqrtf(v / c2) + epsf;
         break;
       case PMX_NADAM:
         phi = (a.b1 * (double)m + (1.0 - a.b1) * (double)g) / c1;
-        psi = sqrtf(v / c2) + a.eps;
+        psi = sqrtf(v / c2) + epsf;
         break;
       case PMX_RADAM:
         phi = (double)m / c1;
         psi = radam_rect ? sqrtf(v / c2) / radam_r : 1.0f;
-        if (a.eps > 0.f) psi = fmaxf(psi, sqrtf(a.eps));
+        if (a.eps > 0.0) psi = fmaxf(psi, (float)sqrt(a.eps));
         break;
       default: {  // AMSGRAD / PADAM / ADAMX
         float vh = v;
@@ -785,9 +786,9 @@ __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
           vh = fmaxf(old, v);
           a.Vhat[i] = vh;
         }
-        if (a.eps > 0.f) vh = fmaxf(vh, a.eps);
+        if (a.eps > 0.0) vh = fmaxf(vh, epsf);
         phi = m;
-        psi = (a.scheme == PMX_PADAM) ? powf(vh, a.p) : sqrtf(vh);
+        psi = (a.scheme == PMX_PADAM) ? powf(vh, pf) : sqrtf(vh);
       }
     }
     const float al = step_at(a.alpha, r, c);

@@ -179,7 +179,7 @@ int pmx_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, dou
 // adaprox moment update + step on caller-owned device arrays (algorithms.py:147-245, :378); *psimax_host = max(Psi)
 int pmx_adaprox_moments(pmx_ctx* ctx, int scheme, const float* G, float* M, float* V, float* Vhat_or_null, float* X,
                         float* Psi, int rows, int cols, const float* alpha_dev, int alpha_mode, float alpha_value,
-                        double b1, double b1_prev, float b2, float eps, float p, int t, float* psimax_host) {
+                        double b1, double b1_prev, double b2, double eps, double p, int t, float* psimax_host) {
   PMX_REQUIRE(ctx && G && M && V && X && Psi && psimax_host, "NULL argument");
   PMX_REQUIRE(scheme >= PMX_ADAM && scheme <= PMX_RADAM, "unknown adaprox scheme");
   float* d_pm = nullptr;

@@ -272,9 +272,6 @@ __global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ 
 
 }  // namespace
 
-// scratch for the per-block partial Gram matrices: one buffer per (context, tall/wide), grown on demand
-static float* g_part[2] = {nullptr, nullptr};
-static size_t g_part_bytes[2] = {0, 0};
 
 int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int cols, bool tall, double* gram,
                 const int* done) {
@@ -290,22 +287,30 @@ int launch_gram(pmx_ctx* ctx, cudaStream_t st, const float* X, int rows, int col
   // enough blocks to keep loads in flight on every SM, few enough that the fp64 reduction stays tiny
   int blocks = (int)(nchunks < (long long)ctx->sm_count * 2 ? nchunks : (long long)ctx->sm_count * 2);
   if (blocks < 1) blocks = 1;
-  const int w = tall ? 1 : 0;
+  // scratch for the per-block partials: owned by the context, one buffer per (tall/wide, stream) so that two
+  // contexts of one process or the two streams of a context never share it; grown on demand
+  const int w = (tall ? 1 : 0) + (st == ctx->aux ? 2 : 0);
   const size_t need = sizeof(float) * (size_t)blocks * C * C;
-  if (need > g_part_bytes[w]) {
-    if (g_part[w]) cudaFree(g_part[w]);
-    if (cudaMalloc((void**)&g_part[w], need) != cudaSuccess) {
+  if (need > ctx->gram_scratch_bytes[w]) {
+    if (ctx->gram_scratch[w]) {
+      cudaStreamSynchronize(st);   // a previous launch may still read the old buffer
+      cudaFree(ctx->gram_scratch[w]);
+      ctx->gram_scratch[w] = nullptr;
+      ctx->gram_scratch_bytes[w] = 0;
+    }
+    if (cudaMalloc((void**)&ctx->gram_scratch[w], need) != cudaSuccess) {
       pmx_set_error("cudaMalloc of the Gram scratch failed");
       return PMX_ERR_CUDA;
     }
-    g_part_bytes[w] = need;
+    ctx->gram_scratch_bytes[w] = need;
   }
+  float* part = ctx->gram_scratch[w];
   if (tall)
-    k_gram<true><<<blocks, 256, smem, st>>>(X, rows, cols, g_part[w], done);
+    k_gram<true><<<blocks, 256, smem, st>>>(X, rows, cols, part, done);
   else
-    k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, g_part[w], done);
+    k_gram<false><<<blocks, 256, smem, st>>>(X, rows, cols, part, done);
   PMX_LAUNCHED(ctx);
-  return launch_gram_reduce(ctx, st, g_part[w], blocks, C, gram, done);
+  return launch_gram_reduce(ctx, st, part, blocks, C, gram, done);
 }
 
 int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,

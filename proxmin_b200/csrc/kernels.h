@@ -54,7 +54,7 @@ struct AdaArgs {
   StepSpec alpha;
   int scheme;
   double b1, b1_prev;  // b1 is a float64 array in the reference (algorithms.py:327-328): M is formed in double
-  float b2, eps, p;
+  double b2, eps, p;   // Python floats in the reference: scalar recipes in double, one rounding to fp32 where they meet an array
   int t;  // it + 1
 };
 int launch_adaprox_moments(pmx_ctx* ctx, const AdaArgs& a);

@@ -125,6 +125,17 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
   return PMX_OK;
 }
 
+// prox_unity(axis=1) on the column-sharded S block divides by a row sum over ALL ranks' columns: not implemented,
+// so a sharded solve must refuse it instead of normalising by the local partial sum
+static int reject_sharded_row_unity(pmx_nmf* h, const ProxChain& chS, const char* what) {
+  const int ax = chain_unity_axis(chS);
+  if (h->ctx->world > 1 && (ax == 1 || ax == 2)) {
+    pmx_set_error("%s: prox_unity(axis=1) on the column-sharded S block needs a cross-rank row sum (not implemented)", what);
+    return PMX_ERR_UNSUPPORTED;
+  }
+  return PMX_OK;
+}
+
 static bool nmf_uses_umma(pmx_nmf* h, int kernel) {
   return kernel == 2 || (kernel == 0 && umma_supported(h->M, h->N, h->K) && (long long)h->M * h->N >= 128LL * 128);
 }
@@ -359,6 +370,7 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   if (h->pgm.check_every <= 0) h->pgm.check_every = 8;
   h->chA = make_chain(&opts->prox_A);
   h->chS = make_chain(&opts->prox_S);
+  PMX_CHECK(reject_sharded_row_unity(h, h->chS, "pgm"));
   h->nest_t = 1.0;  // utils.py:195
   h->it_enqueued = 0;
   if (opts->accelerated) {
@@ -560,6 +572,7 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   h->gram_pending = false;
   h->chA = make_chain(&opts->prox_A);
   h->chS = make_chain(&opts->prox_S);
+  PMX_CHECK(reject_sharded_row_unity(h, h->chS, "adaprox"));
   const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
   const size_t big = mk > kn ? mk : kn;
   float** bufs[] = {&h->MA, &h->VA, &h->MS, &h->VS};
@@ -713,6 +726,7 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
           pmx_set_error("prox_unity(axis=1) on the column-sharded S block needs a cross-rank row sum (not implemented)");
           return PMX_ERR_UNSUPPORTED;
         }
+  PMX_CHECK(reject_sharded_row_unity(h, make_chain(&opts->prox_S), "bsdmm (direct prox_S)"));
   h->bs = *opts;
   h->split_valid = false;
   h->gramS_valid = false;

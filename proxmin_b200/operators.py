@@ -54,6 +54,11 @@ def _apply(X, step, ops):
     return X
 
 
+def _step_gamma(step, gamma):
+    """gamma * step: the parameter of a continuous penalty in units of the step (operators.py:4-14)."""
+    return gamma * step
+
+
 def _rel(type):
     assert type in ["relative", "absolute"]
     return type == "relative"

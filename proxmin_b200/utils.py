@@ -96,6 +96,62 @@ def l2(x):
     return np.sqrt((x ** 2).sum())
 
 
+def get_step_g(step_f, norm_L2, N=1, M=1):
+    """step_g compatible with step_f and ||L||^2 for ADMM / SDMM / bSDMM (utils.py:269-279): scalar host logic."""
+    return step_f * norm_L2 * N * M
+
+
+def get_step_f(step_f, lR2, lS2):
+    """Residual balancing of Boyd (2011) section 3.4.1 (utils.py:282-292; no caller in the reference)."""
+    mu, tau = 10, 2
+    if lR2 > mu * lS2:
+        return step_f * tau
+    if lS2 > mu * lR2:
+        return step_f / tau
+    return step_f
+
+
+def hasNotNone(l):
+    """utils.py:409-418 (no caller in the reference): number of entries from the first one that holds a non-None
+    item onwards."""
+    for i, ll in enumerate(l):
+        if ll is not None and hasattr(ll, "__iter__"):
+            if any(lll is not None for lll in ll):
+                return len(l) - i
+    return 0
+
+
+class ApproximateCache(object):
+    """Strided memoisation of a slow step function (utils.py:124-190): pure host control logic around a user
+    callable.  ``slack`` = relative change that triggers a re-evaluation, ``max_stride`` = longest skip."""
+
+    def __init__(self, func, slack=0.1, max_stride=100):
+        assert slack >= 0 and slack < 1
+        self.func, self.slack, self.max_stride = func, slack, max_stride
+        self.it, self.stride, self.last, self.stored = 0, 1, -1, None
+
+    def __len__(self):
+        return len(self.stride)   # (the reference's __len__ fails the same way: utils.py:163)
+
+    def __call__(self, *args, **kwargs):
+        if self.slack == 0:
+            self.it += 1
+            return self.func(*args, **kwargs)
+        if self.it >= self.last + self.stride:
+            self.last = self.it
+            val = self.func(*args, **kwargs)
+            if self.it > 1 and self.slack > 0:
+                rel_error = np.abs(self.stored - val) / self.stored
+                budget = self.slack / 2
+                if rel_error < budget and rel_error > 0:
+                    self.stride += max(1, int(budget / rel_error * self.stride))
+                    self.stride = min(self.max_stride, self.stride)
+            self.stored = val
+        else:
+            self.it += 1
+        return self.stored
+
+
 class ConstantStep(object):
     """``step_f(X, it=None) -> value``.  A plain callable for any solver; the device ADMM loop recognises
     it and keeps the whole iteration on the GPU (an arbitrary Python step function forces one host

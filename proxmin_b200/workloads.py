@@ -58,6 +58,55 @@ def cfg5(M=4096, N=131072, K=128, seed=99):
     return Y, A0, S0
 
 
+def cfg2_columns(M, N, K, lo, hi, seed=1234, block=4096):
+    """Columns [lo, hi) of the config-2 workload in column-block form (bench.py): the factors A*, A0 come from one
+    generator, every block of ``block`` columns of S*, the noise and S0 from its own generator, so that any
+    partition of the columns over ranks sees the SAME global Y (SCALE runs at N = 1, 2, 4, 8 solve one problem).
+    Noise level 0.01 std(Y) with the analytic std of a sum of K products of uniform(0,1) pairs, sqrt(7K/144)."""
+    rng_a = np.random.default_rng(seed)
+    At = rng_a.random((M, K), dtype=np.float32)
+    A0 = rng_a.random((M, K), dtype=np.float32)
+    sd = np.float32(0.01 * np.sqrt(7.0 * K / 144.0))
+    n = hi - lo
+    Y = np.empty((M, n), dtype=np.float32)
+    S0 = np.empty((K, n), dtype=np.float32)
+    for b in range(lo // block, (hi + block - 1) // block):
+        c0, c1 = b * block, min(N, (b + 1) * block)
+        rng = np.random.default_rng([seed, b])
+        St = rng.random((K, c1 - c0), dtype=np.float32)
+        Yb = At @ St
+        Yb += sd * rng.standard_normal((M, c1 - c0), dtype=np.float32)
+        np.maximum(Yb, 0, out=Yb)
+        S0b = rng.random((K, c1 - c0), dtype=np.float32)
+        a, e = max(lo, c0), min(hi, c1)
+        Y[:, a - lo:e - lo] = Yb[:, a - c0:e - c0]
+        S0[:, a - lo:e - lo] = S0b[:, a - c0:e - c0]
+    return Y, A0, S0
+
+
+def cfg5_columns(M, N, K, lo, hi, seed=99, block=4096):
+    """Columns [lo, hi) of the config-5 workload in column-block form (see cfg2_columns): noiseless Y = A* S*,
+    columns of A* and A0 sum to one."""
+    rng_a = np.random.default_rng(seed)
+    At = rng_a.random((M, K), dtype=np.float32)
+    At /= At.sum(axis=0, keepdims=True)
+    A0 = rng_a.random((M, K), dtype=np.float32)
+    A0 /= A0.sum(axis=0, keepdims=True)
+    n = hi - lo
+    Y = np.empty((M, n), dtype=np.float32)
+    S0 = np.empty((K, n), dtype=np.float32)
+    for b in range(lo // block, (hi + block - 1) // block):
+        c0, c1 = b * block, min(N, (b + 1) * block)
+        rng = np.random.default_rng([seed, b])
+        St = rng.random((K, c1 - c0), dtype=np.float32)
+        Yb = At @ St
+        S0b = rng.random((K, c1 - c0), dtype=np.float32)
+        a, e = max(lo, c0), min(hi, c1)
+        Y[:, a - lo:e - lo] = Yb[:, a - c0:e - c0]
+        S0[:, a - lo:e - lo] = S0b[:, a - c0:e - c0]
+    return Y, A0, S0
+
+
 def shard_columns(N, world, rank, align=1):
     """Column range [lo, hi) of rank ``rank`` when N columns are split over ``world`` ranks.
 

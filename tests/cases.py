@@ -274,6 +274,121 @@ def nmf_bsdmm(api):
 
 
 @case
+def nmf_pgm_cfg1_1000(api):
+    """BASELINE config 1 at the SURVEY 7.3 horizon: 1000 fixed iterations."""
+    Y, A, S = workloads.cfg1()
+    api.nmf.nmf(Y, A, S, max_iter=1000, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_pgm_k96(api):
+    """K > 64 (the tcgen05 kernel's two k-panel configuration; SIMT before it existed): plus / unity_plus."""
+    Y, A, S = workloads.cfg2(192, 512, 96, seed=31)
+    api.nmf.nmf(Y, A, S, prox_A=api.prox_plus, prox_S=api.prox_unity_plus, max_iter=40, e_rel=0)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_bsdmm_k128(api):
+    """BASELINE config 5 scaled down in M and N only: K = 128 like the real thing (6 outer iterations, see nmf_bsdmm)."""
+    Y, A, S = workloads.cfg5(256, 1024, 128, seed=32)
+    proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus, partial(api.prox_soft, thresh=0.01)]]
+    conv = api.nmf.nmf(Y, A, S, algorithm=api.bsdmm, prox_A=api.prox_id, prox_S=api.prox_id,
+                       proxs_g=proxs_g, max_iter=6, e_rel=1e-6)
+    return _pack(api, A, S, {"converged": np.array([bool(c) for c in conv])})
+
+
+@case
+def nmf_adaprox_soft_kvector(api):
+    """Quirk row of SURVEY 8 a-Q: under step_adaprox the step handed to the prox is gamma = Alpha/max(Psi), a K-vector
+    for A and a K x 1 column for S, so a *relative* threshold broadcasts per component (algorithms.py:384-387)."""
+    Y, A, S = workloads.cfg2(96, 256, 8, seed=33)
+    api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", prox_A=partial(api.prox_soft_plus, thresh=0.05),
+                prox_S=partial(api.prox_soft_plus, thresh=0.1), max_iter=30, check_convergence=False)
+    return _pack(api, A, S)
+
+
+@case
+def nmf_adaprox_zero_column(api):
+    """Quirk row: gamma/Alpha is evaluated literally (algorithms.py:384-387) -- an all-zero column of A gives
+    Alpha = 0 there and 0/0 = NaN in the proximal sub-iteration; the NaN pattern is part of parity."""
+    Y, A, S = workloads.cfg2(64, 128, 6, seed=34)
+    A[:, 2] = 0
+    with np.errstate(all="ignore"):
+        api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", max_iter=1, prox_max_iter=5,
+                    check_convergence=False)
+    return _pack(api, A, S)
+
+
+class _Stopper(object):
+    """callback that keeps copies of the iterates it sees and raises StopIteration at iteration `stop_at`"""
+
+    def __init__(self, stop_at=None):
+        self.trace, self.its, self.stop_at = [], [], stop_at
+
+    def __call__(self, *X, it=None):
+        self.trace.append(tuple(np.array(x, copy=True) for x in X))
+        self.its.append(it)
+        if self.stop_at is not None and it == self.stop_at:
+            raise StopIteration
+
+
+@case
+def nmf_callbacks(api):
+    """callback(*X, it=it) at the top of every iteration through the fused NMF loops, utils.Traceback,
+    and StopIteration ending pgm / adaprox cleanly (algorithms.py:90,137-138,368,412-413,802)."""
+    out = {}
+    # pgm + Traceback
+    Y, A, S = workloads.cfg2(64, 160, 6, seed=35)
+    tb = api.utils.Traceback()
+    api.nmf.nmf(Y, A, S, prox_S=api.prox_unity_plus, max_iter=8, e_rel=0, callback=tb)
+    out["pgm_trace_len"] = np.int64(len(tb.trace))
+    out["pgm_trace3_A"], out["pgm_trace3_S"] = tb.trace[3][0], tb.trace[3][1]
+    out["pgm_A"], out["pgm_S"] = A, S
+    # pgm + StopIteration at it == 5: five iterations are executed
+    Y, A, S = workloads.cfg2(64, 160, 6, seed=35)
+    st = _Stopper(stop_at=5)
+    api.nmf.nmf(Y, A, S, max_iter=20, e_rel=0, callback=st)
+    out["pgm_stop_its"] = np.array(st.its, dtype=np.int64)
+    out["pgm_stop_A"] = A
+    # adaprox + StopIteration at it == 4
+    Y, A, S = workloads.cfg2(64, 160, 6, seed=36)
+    st = _Stopper(stop_at=4)
+    api.nmf.nmf(Y, A, S, algorithm=api.adaprox, scheme="amsgrad", max_iter=20, check_convergence=False, callback=st)
+    out["ada_stop_its"] = np.array(st.its, dtype=np.int64)
+    out["ada_stop_A"], out["ada_stop_S"] = A, S
+    out["ada_trace2_S"] = st.trace[2][1]
+    # bsdmm + Traceback
+    Y, A, S = workloads.cfg5(64, 160, 6, seed=37)
+    tb = api.utils.Traceback()
+    proxs_g = [[api.prox_plus, api.prox_unity], [api.prox_plus]]
+    api.nmf.nmf(Y, A, S, algorithm=api.bsdmm, prox_A=api.prox_id, prox_S=api.prox_id, proxs_g=proxs_g, max_iter=4,
+                e_rel=1e-6, callback=tb)
+    out["bsdmm_trace_len"] = np.int64(len(tb.trace))
+    out["bsdmm_trace2_A"] = tb.trace[2][0]
+    out["bsdmm_A"] = A
+    return out
+
+
+@case
+def admm_callback_unstarred(api):
+    """Quirk row: admm / sdmm hand the array itself to the callback, callback(X, it=it) (algorithms.py:480, 605),
+    while pgm / adaprox / bsdmm star the tuple."""
+    b, X = workloads.cfg4(2_000, seed=38)
+    prox_f, step_f, prox_g = lasso_callables(api, b)
+    seen = []
+
+    def cb(*args, it=None):
+        seen.append((len(args), np.ndim(args[0]), np.shape(args[0])[0], it))
+
+    api.admm(X, prox_f, step_f, prox_g=prox_g, max_iter=3, e_rel=1e-12, callback=cb)
+    X2 = np.zeros_like(b)
+    api.sdmm(X2, prox_f, step_f, proxs_g=[prox_g, api.prox_plus], max_iter=3, e_rel=1e-12, callback=cb)
+    return {"seen": np.array(seen, dtype=np.int64), "X": X, "X2": X2}
+
+
+@case
 def grad_and_loss(api):
     Y, A, S = workloads.cfg2(200, 333, 24, seed=21)
     gA, gS = api.nmf.grad_likelihood(A, S, Y=Y)

@@ -83,7 +83,8 @@ def test_grad_loss_lipschitz(product):
     assert abs(got["step_S"] - want["step_S"]) <= 5e-6 * want["step_S"]
 
 
-PGM_CASES = ["nmf_pgm_cfg1", "nmf_pgm_unity", "nmf_pgm_altproj", "nmf_pgm_soft", "nmf_pgm_ragged", "nmf_pgm_accel"]
+PGM_CASES = ["nmf_pgm_cfg1", "nmf_pgm_unity", "nmf_pgm_altproj", "nmf_pgm_soft", "nmf_pgm_ragged", "nmf_pgm_accel",
+             "nmf_pgm_cfg1_1000", "nmf_pgm_k96"]
 
 
 @pytest.mark.parametrize("name", PGM_CASES)
@@ -112,9 +113,7 @@ def test_nmf_pgm_stopping_iteration(product):
     assert_close(got["S"], want["S"], 2e-4, "S")
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: the backtracking callback loop "
-                                        "(device reductions, host line search) has not run on a B200 yet")
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(300)
 def test_nmf_pgm_backtracking(product):
     """PGM with backtracking (algorithms.py:110-127), f = log_likelihood on the device; the same
     five halvings of T as the reference, factors within 2e-4"""
@@ -152,21 +151,21 @@ def test_nmf_adaprox_amsgrad(product):
     got = cases.nmf_adaprox_amsgrad(product)
     assert int(got["iterations"]) == int(want["iterations"])
     assert list(got["sub_iterations"]) == list(want["sub_iterations"])
-    # adaprox normalises the gradient by sqrt(V): ~100x more sensitive than PGM; bound 5e-4
-    assert_close(got["A"], want["A"], 5e-4, "A")
-    assert_close(got["S"], want["S"], 5e-4, "S")
-    assert_close(got["M_A"], want["M_A"], 5e-3, "M_A")
-    assert_close(got["V_S"], want["V_S"], 5e-3, "V_S")
+    # adaprox normalises the gradient by sqrt(V): ~100x more sensitive than PGM; the north-star
+    # bound 1e-4 still holds with the 3xBF16 split (measured 6e-6 .. 2e-5, profiles/r1_mgpu_check_2gpu.txt)
+    assert_close(got["A"], want["A"], 1e-4, "A")
+    assert_close(got["S"], want["S"], 1e-4, "S")
+    assert_close(got["M_A"], want["M_A"], 1e-3, "M_A")
+    assert_close(got["V_S"], want["V_S"], 1e-3, "V_S")
 
 
 def test_nmf_adaprox_amsgrad_unity(product):
     want = load_golden("nmf_adaprox_amsgrad_unity")
     got = cases.nmf_adaprox_amsgrad_unity(product)
     assert int(got["iterations"]) == int(want["iterations"])
-    sub_g, sub_w = list(got["sub_iterations"]), list(want["sub_iterations"])
-    assert all(abs(a - b) <= max(2, 0.02 * b) for a, b in zip(sub_g, sub_w)), (sub_g, sub_w)
-    assert_close(got["A"], want["A"], 1e-3, "A")
-    assert_close(got["S"], want["S"], 1e-3, "S")
+    assert list(got["sub_iterations"]) == list(want["sub_iterations"])
+    assert_close(got["A"], want["A"], 1e-4, "A")
+    assert_close(got["S"], want["S"], 1e-4, "S")
 
 
 def test_nmf_adaprox_schemes(product):
@@ -174,8 +173,9 @@ def test_nmf_adaprox_schemes(product):
     got = cases.nmf_adaprox_schemes(product)
     for scheme in ["adam", "nadam", "padam", "adamx"]:
         assert int(got[scheme + "_iterations"]) == int(want[scheme + "_iterations"]), scheme
-        assert_close(got[scheme + "_A"], want[scheme + "_A"], 1e-3, scheme + ":A")
-        assert_close(got[scheme + "_S"], want[scheme + "_S"], 1e-3, scheme + ":S")
+        assert list(got[scheme + "_sub"]) == list(want[scheme + "_sub"]), scheme
+        assert_close(got[scheme + "_A"], want[scheme + "_A"], 1e-4, scheme + ":A")
+        assert_close(got[scheme + "_S"], want[scheme + "_S"], 1e-4, scheme + ":S")
 
 
 def test_nmf_bsdmm(product):
@@ -185,6 +185,113 @@ def test_nmf_bsdmm(product):
     assert np.array_equal(got["converged"], want["converged"])
     assert_close(got["A"], want["A"], 5e-4, "A")   # 6 iterations; see cases.nmf_bsdmm for the horizon
     assert_close(got["S"], want["S"], 5e-4, "S")
+
+
+def test_nmf_bsdmm_k128(product):
+    """BASELINE config 5's K = 128 (scaled down in M, N only): the K > 64 gradient path under bsdmm"""
+    want = load_golden("nmf_bsdmm_k128")
+    got = cases.nmf_bsdmm_k128(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert np.array_equal(got["converged"], want["converged"])
+    assert_close(got["A"], want["A"], 5e-4, "A")
+    assert_close(got["S"], want["S"], 5e-4, "S")
+
+
+def test_nmf_adaprox_soft_kvector(product):
+    """relative thresholds under step_adaprox: the prox step is the K-vector gamma (SURVEY 8 a-Q)"""
+    want = load_golden("nmf_adaprox_soft_kvector")
+    got = cases.nmf_adaprox_soft_kvector(product)
+    assert int(got["iterations"]) == int(want["iterations"])
+    assert list(got["sub_iterations"]) == list(want["sub_iterations"])
+    assert_close(got["A"], want["A"], 1e-4, "A")
+    assert_close(got["S"], want["S"], 1e-4, "S")
+    assert_same_support(got["A"], want["A"], "A", guard=1e-4)
+    assert_same_support(got["S"], want["S"], "S", guard=1e-4)
+
+
+def test_nmf_adaprox_zero_column_nan(product):
+    """gamma/Alpha = 0/0 for an all-zero column of A (SURVEY 8 a-Q): same NaN pattern, same sub-iteration counts"""
+    want = load_golden("nmf_adaprox_zero_column")
+    got = cases.nmf_adaprox_zero_column(product)
+    assert np.isnan(want["A"][:, 2]).all() and not np.isnan(want["S"]).any()   # what the reference does
+    assert list(got["sub_iterations"]) == list(want["sub_iterations"])
+    assert_close(got["A"], want["A"], 1e-5, "A")
+    assert_close(got["S"], want["S"], 1e-5, "S")
+
+
+def test_nmf_callbacks_through_fused_loops(product):
+    """callback(*X, it=), utils.Traceback and StopIteration through the fused pgm / adaprox / bsdmm loops"""
+    want = load_golden("nmf_callbacks")
+    got = cases.nmf_callbacks(product)
+    for k in ("pgm_trace_len", "bsdmm_trace_len"):
+        assert int(got[k]) == int(want[k]), k
+    for k in ("pgm_stop_its", "ada_stop_its"):
+        assert list(got[k]) == list(want[k]), k
+    for k in ("pgm_trace3_A", "pgm_trace3_S", "pgm_A", "pgm_S", "pgm_stop_A", "ada_stop_A", "ada_stop_S", "ada_trace2_S"):
+        assert_close(got[k], want[k], 1e-4, k)
+    for k in ("bsdmm_trace2_A", "bsdmm_A"):
+        assert_close(got[k], want[k], 5e-4, k)
+
+
+def test_admm_callback_unstarred(product):
+    """admm / sdmm call callback(X, it=it) with the array itself (algorithms.py:480, 605)"""
+    want = load_golden("admm_callback_unstarred")
+    got = cases.admm_callback_unstarred(product)
+    assert np.array_equal(got["seen"], want["seen"])
+    assert_close(got["X"], want["X"], 1e-6, "X")
+    assert_close(got["X2"], want["X2"], 1e-6, "X2")
+
+
+# ---------------------------------------------------------------- horizons of SURVEY 7.3 / full-size stripe, oracle run live
+def _oracle_vs_product(product, Y, A0, S0, **kw):
+    orc = apis.oracle()
+    Ao, So = A0.copy(), S0.copy()
+    ro = orc.nmf.nmf(Y, Ao, So, **{k: (getattr(orc, v[1:]) if isinstance(v, str) and v.startswith("@") else v)
+                                   for k, v in kw.items()})
+    no = orc.iterations()
+    Ap, Sp = A0.copy(), S0.copy()
+    rp = product.nmf.nmf(Y, Ap, Sp, **{k: (getattr(product, v[1:]) if isinstance(v, str) and v.startswith("@") else v)
+                                       for k, v in kw.items()})
+    return (Ao, So, no, ro), (Ap, Sp, product.iterations(), rp)
+
+
+def test_cfg2_full_rows_stripe_vs_oracle(product):
+    """BASELINE config 2 at its own M and K: a 4096-column stripe of the 8192 x 65536 problem (the fused kernel is
+    stripe-local), 3 PGM iterations plus / unity_plus against the oracle run live; factors <= 1e-4"""
+    from proxmin_b200 import workloads
+
+    Y, A0, S0 = workloads.cfg2(8192, 4096, 64, seed=1234)
+    (Ao, So, no, _), (Ap, Sp, npd, _) = _oracle_vs_product(product, Y, A0, S0, prox_A="@prox_plus",
+                                                           prox_S="@prox_unity_plus", max_iter=3, e_rel=0)
+    assert no[0] == npd[0] == 3
+    assert_close(Ap, Ao, 1e-4, "A")
+    assert_close(Sp, So, 1e-4, "S")
+    assert_same_support(Sp, So, "S", guard=1e-4)
+
+
+def test_pgm_horizon_1024x8192_100it(product):
+    """SURVEY 7.3 horizon for the config-2 recipe: 1024 x 8192, K = 64, 100 iterations, plus / unity_plus"""
+    from proxmin_b200 import workloads
+
+    Y, A0, S0 = workloads.cfg2(1024, 8192, 64, seed=77)
+    (Ao, So, no, _), (Ap, Sp, npd, _) = _oracle_vs_product(product, Y, A0, S0, prox_A="@prox_plus",
+                                                           prox_S="@prox_unity_plus", max_iter=100, e_rel=0)
+    assert no[0] == npd[0] == 100
+    assert_close(Ap, Ao, 1e-4, "A")
+    assert_close(Sp, So, 1e-4, "S")
+
+
+def test_amsgrad_horizon_1024x8192_100it(product):
+    """SURVEY 7.3 horizon for config 3: adaprox / AMSGrad, plus / plus, 100 iterations; sub-iteration counts equal"""
+    from proxmin_b200 import workloads
+
+    Y, A0, S0 = workloads.cfg2(1024, 8192, 64, seed=78)
+    (Ao, So, no, _), (Ap, Sp, npd, _) = _oracle_vs_product(product, Y, A0, S0, algorithm="@adaprox", scheme="amsgrad",
+                                                           max_iter=100, check_convergence=False)
+    assert no[0] == npd[0] == 100
+    assert list(no[1]) == list(npd[1]), (no, npd)
+    assert_close(Ap, Ao, 1e-4, "A")
+    assert_close(Sp, So, 1e-4, "S")
 
 
 # ---------------------------------------------------------------- ADMM / SDMM
@@ -239,7 +346,7 @@ def test_sdmm_lasso(product):
 
 # ---------------------------------------------------------------- tcgen05 kernel vs the SIMT kernel
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 512, 8), (300, 1000, 20), (77, 204, 5), (1024, 2048, 64), (130, 333, 7),
-                                   (257, 129, 33)])
+                                   (257, 129, 33), (256, 512, 96), (300, 700, 128), (130, 333, 65), (1024, 2048, 128)])
 def test_tcgen05_gradient_matches_fp64(shape):
     """3xBF16-split tensor-core GEMMs: gradients within 2e-5 (relative Frobenius) of an fp64 evaluation"""
     import ctypes as C
