@@ -7,7 +7,10 @@
 // operands miss the 1e-4 parity target by 10-100x while this split clears it with margin.
 // A and S arrive pre-split (k_split_bf16); R is split in the epilogue registers.
 //
-// Tiling: a tile is 128 rows (m) x 128 columns (n) of Y; K <= 64 (operands zero-padded to 64).
+// Tiling: a tile is 128 rows (m) x 128 columns (n) of Y.  K <= 64: operands zero-padded to 64 (KH = 1).
+// 64 < K <= 128 (KH = 2, BASELINE config 5): operands zero-padded to 128 and handled as two 64-deep k-halves -- the
+// residual GEMM accumulates both halves into the same accumulator, the gradient GEMMs run per half from the same
+// R^T (see "K > 64" below).
 // The tile sequence is m-block major (all 128-column stripes of a 128-row block are consecutive) and
 // is cut into gridDim.x contiguous, equally long ranges -- one persistent CTA per SM -- so the load is
 // balanced to within one tile.
@@ -26,14 +29,22 @@
 //
 // Shared memory (all operands are "panels": rows of 128 bytes, 128B-swizzled in 8-row atoms, which
 // the same bytes can be read as a K-major or an MN-major UMMA operand):
-//   S_hi,S_lo  [2 n-panels][64 k-rows][128B] x 3 slots  96 KB   per tile      (TMA)
-//   A_hi,A_lo  [128 m-rows][128B]              32 KB   per row segment   (TMA)
-//   R_hi,R_lo  [2 m-panels][128 n-rows][128B]  64 KB   per tile          (residual warps write)
-// TMEM (512 columns): residual accumulator 2 x 128, G_S^T accumulator 2 x 64, G_A accumulator [hh|hl] 128.
+//   S_hi,S_lo  [2 n-panels][64 k-rows][128B] x 3 slots  96 KB   per tile (per k-half)   (TMA)
+//   A_hi,A_lo  [128 m-rows][128B] x KH            32 KB x KH   per row segment          (TMA)
+//   R_hi,R_lo  [2 m-panels][128 n-rows][128B]     64 KB   per tile          (residual warps write)
+// TMEM (512 columns): residual accumulator 2 x 128; KH = 1: G_S^T accumulator 2 x 64, G_A accumulator [hh|hl] 128;
+// KH = 2: G_S^T accumulator 128 (single buffer), G_A accumulator 2 x 64 (one per k-half, three terms summed in place).
 //
-// Warp roles (512 threads): warp 0 = TMA producer, warps 1, 2, 3 = MMA issuers (residual / G_S / G_A; warp 2
-// also allocates the tensor memory), warps 4..11 = residual warps (TMEM accumulator -> R^T in TMEM and SMEM; two warps
-// share each TMEM lane quarter and split the column chunks), warps 12..15 = gradient flush warps.
+// Warp roles (640 threads): warp 0 = TMA producer, warps 1, 2, 3 = MMA issuers (residual / G_S / G_A; warp 2
+// also allocates the tensor memory), warps 4..19 = sixteen residual + flush warps (4 TMEM lane quarters x 4 column
+// chunks): TMEM accumulator -> R^T in TMEM and SMEM, then the red.add flush of the previous tile's G_S^T.
+//
+// K > 64 (KH = 2).  Shared memory cannot hold two-deep S tiles of 128 k-rows next to the 64 KB A tile and the 64 KB
+// R^T copy, so the S ring holds k-HALF tiles (same 32 KB slot layout) and every half is loaded twice per tile: once
+// for the residual GEMM (released by issuer 1) and once, a tile later, for the G_A GEMM (released by issuer 3).  The
+// ring is one FIFO over both consumers:  R(0,0) R(0,1) | R(t+1,0) R(t+1,1) G(t,0) G(t,1) | ...   (R = residual use,
+// G = G_A use, second index = k-half); every consumer derives slot and phase from the use index.  G_S^T[n, 0..127]
+// takes the A tile of both halves as ONE N = 128 MN-major B operand (the halves are 16 KB apart = the LBO).
 #include <cuda_bf16.h>
 #include <type_traits>
 #include <stdlib.h>
@@ -50,11 +61,14 @@ constexpr uint32_t PANEL_R = 128 * 128;   // bytes of one R^T / A panel (128 row
 
 // shared-memory map (offsets from the 1024-aligned base)
 constexpr uint32_t OFF_S = 0;                               // slot s at OFF_S + s*4*PANEL_S (see S slot layout below)
-constexpr uint32_t OFF_A = OFF_S + S_SLOTS * 4 * PANEL_S;   // A_hi, then A_lo (one m-block at a time)
-constexpr uint32_t OFF_R_HI = OFF_A + 2 * PANEL_R;
-constexpr uint32_t OFF_R_LO = OFF_R_HI + 2 * PANEL_R;
-constexpr uint32_t OFF_BAR = OFF_R_LO + 2 * PANEL_R;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;       // barriers + alignment slack
+constexpr uint32_t OFF_A = OFF_S + S_SLOTS * 4 * PANEL_S;   // A_hi[kh] at OFF_A + kh*PANEL_R, A_lo[kh] at OFF_A + (KH + kh)*PANEL_R
+template <int KH> struct SmemMap {
+  static constexpr uint32_t R_HI = OFF_A + KH * 2 * PANEL_R;
+  static constexpr uint32_t R_LO = R_HI + 2 * PANEL_R;
+  static constexpr uint32_t BAR = R_LO + 2 * PANEL_R;
+  static constexpr uint32_t BYTES = BAR + 512 + 1024;       // barriers + alignment slack
+};
+static_assert(SmemMap<2>::BYTES <= 232448, "K = 128 configuration exceeds the 227 KB of shared memory per CTA");
 
 enum {  // mbarrier indices
   B_A_FULL = 0, B_A_EMPTY, B_S_FULL, B_S_EMPTY = B_S_FULL + S_SLOTS, B_ACC_FULL = B_S_EMPTY + S_SLOTS,
@@ -248,6 +262,7 @@ struct Params {
   float* GS;
   double* loss;
   const int* done;
+  int want_ga, want_gs;   // 0: that gradient GEMM and its flush are skipped (bsdmm needs one gradient per pass, the loss none)
   long long* trace;       // debug: clock64 timeline of CTA 0 (env PMX_TRACE), [role][tile][event]
   int ablate;             // debug/timing only (env PMX_ABLATE): bit0 no MMA1, 1 no MMA2, 2 no MMA3, 3 no Y read, 4 no R store, 5 no G_S flush, 7 no L2 hint on the Y loads
 };
@@ -276,13 +291,26 @@ struct TilePos {
   }
 };
 
+// KH = 2: position of a use in the S-ring FIFO  R(0,0) R(0,1) | R(t+1,0) R(t+1,1) G(t,0) G(t,1) | ...
+// (without the G_A GEMM only the R uses exist)
+__device__ __forceinline__ uint32_t ring_use_R(int t, int kh, bool with_g) {
+  if (!with_g) return 2u * t + kh;
+  return t == 0 ? (uint32_t)kh : (uint32_t)(4 * t - 2 + kh);
+}
+__device__ __forceinline__ uint32_t ring_use_G(int t, int kh, int ntiles) {
+  return (uint32_t)((t == ntiles - 1 ? 4 * t + 2 : 4 * t + 4) + kh);
+}
+
+// KH: number of 64-deep k-halves (1: K <= 64, 2: K <= 128)
 // LOSS: accumulate |R|^2 / 2 (nmf.py:25); DBG: timing ablations and the clock64 trace (never used for results)
-template <bool LOSS, bool DBG>
+template <int KH, bool LOSS, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
             const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmShi,
             const __grid_constant__ CUtensorMap tmSlo, const Params p) {
   if (p.done && *p.done) return;
+  constexpr uint32_t OFF_R_HI = SmemMap<KH>::R_HI, OFF_R_LO = SmemMap<KH>::R_LO, OFF_BAR = SmemMap<KH>::BAR;
+  constexpr int KPT = KP * KH;   // padded K
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -303,6 +331,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
   TilePos pos0;
   pos0.mb = (int)(g_begin / NS);
   pos0.st = (int)(g_begin - (long long)pos0.mb * NS);
+  const bool want_ga = p.want_ga != 0, want_gs = p.want_gs != 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
@@ -330,8 +359,11 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
   auto first_in_seg = [&](int t, const TilePos& q) { return t == 0 || q.st == 0; };
   auto last_in_seg = [&](int t, const TilePos& q) { return t == ntiles - 1 || q.st == NS - 1; };
   // S slot layout: n-panel pn (64 columns) = [S_hi 64 k-rows | S_lo 64 k-rows] -> 16 KB per panel, so that
-  // [S_hi; S_lo] is one 128-row K-major operand (the "stacked" N = 128 operand of the G_A GEMM)
+  // [S_hi; S_lo] is one 128-row K-major operand (the "stacked" N = 128 operand of the G_A GEMM, KH = 1)
   constexpr uint32_t S_SLOT = 4 * PANEL_S, S_PANEL = 2 * PANEL_S;
+  // A tile: hi half kh at a_hi(kh), lo half at a_lo(kh); the two k-halves of one precision are PANEL_R apart
+  auto a_hi = [&](int kh) { return base + OFF_A + (uint32_t)kh * PANEL_R; };
+  auto a_lo = [&](int kh) { return base + OFF_A + (uint32_t)(KH + kh) * PANEL_R; };
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -341,33 +373,65 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     // measured and only slowed the kernel down: the plain loads already keep HBM busy)
     uint32_t seg = 0;
     const uint64_t pol_keep = l2_policy_evict_last();
-    TilePos pos = pos0;
     uint32_t slot = 0, use = 0;
-    for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
-      const int m0 = pos.mb * TILE_M, n0 = pos.st * TILE_N;
+    // one S-ring slot: the 64-deep k-half kh of the S tile at column n0
+    auto load_s = [&](int n0, int kh) {
       mbar_wait(bar(B_S_EMPTY + slot), (use & 1) ^ 1);
       if (lane == 0) {
         mbar_expect_tx(bar(B_S_FULL + slot), 4 * PANEL_S);
         const uint32_t sb = base + OFF_S + slot * S_SLOT;
-        tma_load_2d_hint(sb, &tmShi, n0, 0, bar(B_S_FULL + slot), pol_keep);
-        tma_load_2d_hint(sb + PANEL_S, &tmSlo, n0, 0, bar(B_S_FULL + slot), pol_keep);
-        tma_load_2d_hint(sb + S_PANEL, &tmShi, n0 + 64, 0, bar(B_S_FULL + slot), pol_keep);
-        tma_load_2d_hint(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, 0, bar(B_S_FULL + slot), pol_keep);
-      }
-      TR(0, t, 0);
-      if (first_in_seg(t, pos)) {
-        mbar_wait(bar(B_A_EMPTY), (seg & 1) ^ 1);
-        if (lane == 0) {
-          mbar_expect_tx(bar(B_A_FULL), 2 * PANEL_R);
-          tma_load_2d(base + OFF_A, &tmAhi, 0, m0, bar(B_A_FULL));
-          tma_load_2d(base + OFF_A + PANEL_R, &tmAlo, 0, m0, bar(B_A_FULL));
-        }
-        ++seg;
+        tma_load_2d_hint(sb, &tmShi, n0, kh * KP, bar(B_S_FULL + slot), pol_keep);
+        tma_load_2d_hint(sb + PANEL_S, &tmSlo, n0, kh * KP, bar(B_S_FULL + slot), pol_keep);
+        tma_load_2d_hint(sb + S_PANEL, &tmShi, n0 + 64, kh * KP, bar(B_S_FULL + slot), pol_keep);
+        tma_load_2d_hint(sb + S_PANEL + PANEL_S, &tmSlo, n0 + 64, kh * KP, bar(B_S_FULL + slot), pol_keep);
       }
       __syncwarp();
       if (++slot == S_SLOTS) {
         slot = 0;
         ++use;
+      }
+    };
+    auto load_a = [&](int m0) {
+      mbar_wait(bar(B_A_EMPTY), (seg & 1) ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(bar(B_A_FULL), KH * 2 * PANEL_R);
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh) {
+          tma_load_2d(a_hi(kh), &tmAhi, kh * KP, m0, bar(B_A_FULL));
+          tma_load_2d(a_lo(kh), &tmAlo, kh * KP, m0, bar(B_A_FULL));
+        }
+      }
+      ++seg;
+      __syncwarp();
+    };
+    if constexpr (KH == 1) {
+      TilePos pos = pos0;
+      for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
+        load_s(pos.st * TILE_N, 0);
+        TR(0, t, 0);
+        if (first_in_seg(t, pos)) load_a(pos.mb * TILE_M);
+      }
+    } else {
+      // FIFO  R(0,0) R(0,1) | R(t+1,0) R(t+1,1) G(t,0) G(t,1) | ...  (see the file header); the A tile of a row segment
+      // is requested right after the first residual half of its first tile
+      TilePos pos = pos0, nxt = pos0;
+      if (ntiles > 0) {
+        load_s(pos.st * TILE_N, 0);
+        load_a(pos.mb * TILE_M);
+        load_s(pos.st * TILE_N, 1);
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        nxt.next(NS);
+        if (t + 1 < ntiles) {
+          load_s(nxt.st * TILE_N, 0);
+          if (first_in_seg(t + 1, nxt)) load_a(nxt.mb * TILE_M);
+          load_s(nxt.st * TILE_N, 1);
+        }
+        if (want_ga) {
+          load_s(pos.st * TILE_N, 0);
+          load_s(pos.st * TILE_N, 1);
+        }
+        pos = nxt;
       }
     }
   } else if (warp == 1) {
@@ -377,83 +441,99 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     // Three issuer warps (residual / G_S / G_A), each blocking only on its own dependencies; all 32 lanes run the
     // loop and one elected lane issues.
     constexpr uint32_t ID_RES = make_idesc(128, 128, 1, 0);
-    const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
     uint32_t seg_full = 0, sslot = 0, suse = 0;
     TilePos pos = pos0;
     for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
       const uint32_t slot = t & 1;
-      mbar_wait(bar(B_S_FULL + sslot), suse & 1);
-      if (first_in_seg(t, pos)) {
-        mbar_wait(bar(B_A_FULL), seg_full & 1);
-        ++seg_full;
-      }
-      mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
-      tc_fence_after();
-      TR(1, t, 0);
-      const uint32_t sb = base + OFF_S + sslot * S_SLOT;
       const uint32_t d = tmem + TM_ACC + slot * 128;
-      // acc = S_hi^T A_hi^T + S_lo^T A_hi^T + S_hi^T A_lo^T      (K = 64: 4 k-steps of 16)
-      const uint32_t s_src[3] = {sb, sb + PANEL_S, sb};
-      const uint32_t a_src[3] = {a_hi, a_hi, a_lo};
 #pragma unroll
-      for (int term = 0; term < 3; ++term)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          if (ABL(1)) continue;
-          const uint64_t ad = make_desc(s_src[term] + ks * 2048, S_PANEL, 1024);      // MN-major: LBO = next 64 n
-          const uint64_t bd = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major, 128 m-rows
-          umma_ss_e(d, ad, bd, ID_RES, (term | ks) ? 1u : 0u);
+      for (int kh = 0; kh < KH; ++kh) {
+        if constexpr (KH == 2) {
+          const uint32_t u = ring_use_R(t, kh, want_ga);
+          sslot = u % S_SLOTS;
+          suse = u / S_SLOTS;
         }
+        mbar_wait(bar(B_S_FULL + sslot), suse & 1);
+        if (kh == 0) {
+          if (first_in_seg(t, pos)) {
+            mbar_wait(bar(B_A_FULL), seg_full & 1);
+            ++seg_full;
+          }
+          mbar_wait(bar(B_ACC_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+        }
+        tc_fence_after();
+        if (kh == 0) TR(1, t, 0);
+        const uint32_t sb = base + OFF_S + sslot * S_SLOT;
+        // acc += S_hi^T A_hi^T + S_lo^T A_hi^T + S_hi^T A_lo^T      (64 k of this half: 4 k-steps of 16)
+        const uint32_t s_src[3] = {sb, sb + PANEL_S, sb};
+        const uint32_t a_src[3] = {a_hi(kh), a_hi(kh), a_lo(kh)};
+#pragma unroll
+        for (int term = 0; term < 3; ++term)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ABL(1)) continue;
+            const uint64_t ad = make_desc(s_src[term] + ks * 2048, S_PANEL, 1024);      // MN-major: LBO = next 64 n
+            const uint64_t bd = make_desc(a_src[term] + ks * 32, 16, 1024);             // K-major, 128 m-rows
+            umma_ss_e(d, ad, bd, ID_RES, (kh | term | ks) ? 1u : 0u);
+          }
+        if constexpr (KH == 2) tc_commit_e(bar(B_S_EMPTY + sslot));   // this half-tile is reloaded for the G_A GEMM
+      }
       tc_commit_e(bar(B_ACC_FULL + slot));
       TR(1, t, 1);
       if (last_in_seg(t, pos)) tc_commit_e(bar(B_A_EMPTY));   // residual GEMMs of this segment are done with the A tile
-      if (++sslot == S_SLOTS) {
-        sslot = 0;
-        ++suse;
+      if constexpr (KH == 1) {
+        if (++sslot == S_SLOTS) {
+          sslot = 0;
+          ++suse;
+        }
       }
     }
   } else if (warp == 2) {
     // ============================== MMA issuer 2: G_S GEMM (after the TMEM allocation above) ================
-    // G_S^T[n, k] = R_hi^T A_hi + R_hi^T A_lo + R_lo^T A_hi   (M = n, N = k = 64, K = m: 8 k-steps).  R^T (bf16 hi/lo)
+    // G_S^T[n, k] = R_hi^T A_hi + R_hi^T A_lo + R_lo^T A_hi   (M = n, N = k, K = m: 8 k-steps).  R^T (bf16 hi/lo)
     // sits in the columns of the residual accumulator it was computed from: every 16 accumulator columns become
     // [hi 8 cols | lo 8 cols] of packed bf16 pairs -> the A operand comes from tensor memory, only the A tile
-    // (MN-major B operand) is read from shared memory.
-    constexpr uint32_t ID_GS = make_idesc(128, 64, 0, 1);
-    const uint32_t a_hi = base + OFF_A, a_lo = a_hi + PANEL_R;
+    // (MN-major B operand) is read from shared memory.  KH = 1: N = 64, double-buffered accumulator; KH = 2: the two
+    // k-halves of the A tile are one N = 128 operand (LBO = distance of the halves), single accumulator.
+    constexpr uint32_t ID_GS = make_idesc(128, 64 * KH, 0, 1);
     uint32_t seg_full = 0;
     TilePos pos = pos0;
     for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
       const uint32_t slot = t & 1;
+      const uint32_t gslot = KH == 1 ? slot : 0u, guse = KH == 1 ? (uint32_t)(t >> 1) : (uint32_t)t;
       if (first_in_seg(t, pos)) {
         mbar_wait(bar(B_A_FULL), seg_full & 1);          // already complete (MMA1 consumed it): visibility only
         ++seg_full;
       }
       mbar_wait(bar(B_RT_FULL + slot), (t >> 1) & 1);
-      mbar_wait(bar(B_GS_EMPTY + slot), ((t >> 1) & 1) ^ 1);
+      mbar_wait(bar(B_GS_EMPTY + gslot), (guse & 1) ^ 1);
       tc_fence_after();
       TR(1, t, 2);
-      const uint32_t d = tmem + TM_GS + slot * 64;
+      const uint32_t d = tmem + TM_GS + gslot * 64;
       const uint32_t racc = tmem + TM_ACC + slot * 128;
       const uint32_t r_off[3] = {0, 0, 8};               // R_hi, R_hi, R_lo pairs of a k-step's 16 columns
-      const uint32_t a_src[3] = {a_hi, a_lo, a_hi};
+      const uint32_t a_src[3] = {a_hi(0), a_lo(0), a_hi(0)};
+      if (want_gs) {
 #pragma unroll
-      for (int term = 0; term < 3; ++term)
+        for (int term = 0; term < 3; ++term)
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          if (ABL(2)) continue;
-          const uint32_t at = racc + ks * 16 + r_off[term];
-          const uint64_t bd = make_desc(a_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major, one 64-wide atom
-          umma_ts_e(d, at, bd, ID_GS, (term | ks) ? 1u : 0u);
-        }
-      tc_commit_e(bar(B_GS_FULL + slot));
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ABL(2)) continue;
+            const uint32_t at = racc + ks * 16 + r_off[term];
+            const uint64_t bd = make_desc(a_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major, 64-wide atoms PANEL_R apart
+            umma_ts_e(d, at, bd, ID_GS, (term | ks) ? 1u : 0u);
+          }
+      }
+      tc_commit_e(bar(B_GS_FULL + gslot));
       tc_commit_e(bar(B_ACC_EMPTY + slot));  // MMA1(t+2) may overwrite these columns once R^T(t) has been consumed
       TR(1, t, 3);
       if (last_in_seg(t, pos)) tc_commit_e(bar(B_A_EMPTY));
     }
   } else if (warp == 3) {
     // ============================== MMA issuer 3: G_A GEMM ==============================
-    // G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (M = m, K = n: 8 k-steps).  R comes from the
-    // shared-memory copy of R^T (MN-major A operand), the stacked S slot is the K-major B operand.
+    // KH = 1: G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (M = m, K = n: 8 k-steps).  R comes
+    // from the shared-memory copy of R^T (MN-major A operand), the stacked S slot is the K-major B operand.
+    // KH = 2: per k-half, G_A[m, half] += R_hi S_hi^T + R_hi S_lo^T + R_lo S_hi^T (N = 64 each, summed in place).
     constexpr uint32_t ID_GA2 = make_idesc(128, 128, 1, 0);
     constexpr uint32_t ID_GA1 = make_idesc(128, 64, 1, 0);
     const uint32_t r_hi = base + OFF_R_HI, r_lo = base + OFF_R_LO;
@@ -461,50 +541,86 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     TilePos pos = pos0;
     for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
       const bool first = first_in_seg(t, pos);
-      mbar_wait(bar(B_S_FULL + sslot), suse & 1);    // already complete (MMA1(t) consumed it): visibility only
-      mbar_wait(bar(B_RS_FULL), t & 1);
-      if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
-      tc_fence_after();
-      TR(2, t, 0);
-      const uint32_t sb = base + OFF_S + sslot * S_SLOT;
-      const uint32_t d = tmem + TM_GA;
+      if constexpr (KH == 1) {
+        mbar_wait(bar(B_S_FULL + sslot), suse & 1);    // already complete (MMA1(t) consumed it): visibility only
+        mbar_wait(bar(B_RS_FULL), t & 1);
+        if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
+        tc_fence_after();
+        TR(2, t, 0);
+        const uint32_t sb = base + OFF_S + sslot * S_SLOT;
+        const uint32_t d = tmem + TM_GA;
+        if (want_ga) {
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        if (ABL(4)) continue;
-        const uint64_t ad = make_desc(r_hi + ks * 2048, PANEL_R, 1024);                        // MN-major: LBO = next 64 m
-        const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);     // K-major, 128 rows
-        umma_ss_e(d, ad, bd, ID_GA2, (!first || ks) ? 1u : 0u);
-      }
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ABL(4)) continue;
+            const uint64_t ad = make_desc(r_hi + ks * 2048, PANEL_R, 1024);                        // MN-major: LBO = next 64 m
+            const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);     // K-major, 128 rows
+            umma_ss_e(d, ad, bd, ID_GA2, (!first || ks) ? 1u : 0u);
+          }
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        if (ABL(4)) continue;
-        const uint64_t ad = make_desc(r_lo + ks * 2048, PANEL_R, 1024);
-        const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);     // K-major, rows 0..63
-        umma_ss_e(d, ad, bd, ID_GA1, 1u);
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ABL(4)) continue;
+            const uint64_t ad = make_desc(r_lo + ks * 2048, PANEL_R, 1024);
+            const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + (ks & 3) * 32, 16, 1024);     // K-major, rows 0..63
+            umma_ss_e(d, ad, bd, ID_GA1, 1u);
+          }
+        }
+        tc_commit_e(bar(B_RS_EMPTY));
+        tc_commit_e(bar(B_S_EMPTY + sslot));   // S(t) was last used here
+        if (++sslot == S_SLOTS) {
+          sslot = 0;
+          ++suse;
+        }
+      } else {
+        mbar_wait(bar(B_RS_FULL), t & 1);
+        if (first) mbar_wait(bar(B_GA_EMPTY), (seg & 1) ^ 1);
+        if (want_ga) {
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint32_t u = ring_use_G(t, kh, ntiles);
+            sslot = u % S_SLOTS;
+            suse = u / S_SLOTS;
+            mbar_wait(bar(B_S_FULL + sslot), suse & 1);
+            tc_fence_after();
+            if (kh == 0) TR(2, t, 0);
+            const uint32_t sb = base + OFF_S + sslot * S_SLOT;
+            const uint32_t d = tmem + TM_GA + kh * 64;
+            const uint32_t r_src[3] = {r_hi, r_hi, r_lo};
+            const uint32_t s_off[3] = {0, PANEL_S, 0};         // S_hi rows, S_lo rows, S_hi rows of the n-panel
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                if (ABL(4)) continue;
+                const uint64_t ad = make_desc(r_src[term] + ks * 2048, PANEL_R, 1024);
+                const uint64_t bd = make_desc(sb + (ks >> 2) * S_PANEL + s_off[term] + (ks & 3) * 32, 16, 1024);   // K-major, 64 k-rows
+                umma_ss_e(d, ad, bd, ID_GA1, (!first || term || ks) ? 1u : 0u);
+              }
+            tc_commit_e(bar(B_S_EMPTY + sslot));
+          }
+        } else {
+          tc_fence_after();
+        }
+        tc_commit_e(bar(B_RS_EMPTY));
       }
-      tc_commit_e(bar(B_RS_EMPTY));
-      tc_commit_e(bar(B_S_EMPTY + sslot));   // S(t) was last used here
       TR(2, t, 1);
       if (last_in_seg(t, pos)) {
         tc_commit_e(bar(B_GA_FULL));
         ++seg;
-      }
-      if (++sslot == S_SLOTS) {
-        sslot = 0;
-        ++suse;
       }
     }
   } else {
     // ============================== residual + flush warps (16) ==============================
     // Warp (q4, grp): TMEM lane quarter q4 (the 32 columns n = 32 q4 + lane of the tile), 32-row chunk grp of the
     // accumulator columns.  Per tile: residual chunk -> R^T (TMEM, registers -> SMEM), then the flush of the previous
-    // tile's G_S^T (16 of its 64 k-columns) while the tensor pipe works on this one.
+    // tile's G_S^T (a quarter of its k-columns) while the tensor pipe works on this one.
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
     const int grp = (warp - 4) >> 2;         // m-chunk of the residual / k-quarter of the flushes
     const int row = q4 * 32 + lane;          // column n of the tile = accumulator lane (row m for the G_A flush)
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const uint64_t pol = ABL(128) ? l2_policy_normal() : l2_policy_evict_first();
     const int K = p.K, N = p.N, M = p.M, ldY = p.ldY;
+    constexpr int KQ = 16 * KH;              // gradient columns (k) this warp flushes: [grp * KQ, grp * KQ + KQ)
     float* const GA = p.ga_epoch ? p.GA + (size_t)((*p.ga_epoch + 1u) & 1u) * p.ga_stride : p.GA;
     // shared-memory destinations of this thread's R^T chunk (row n, 128B-swizzled 16-byte chunks): loop invariant
     uint8_t* const rh = base_ptr + OFF_R_HI + (grp >> 1) * PANEL_R + row * 128;
@@ -540,62 +656,83 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         }
       }
     };
-    // G_S^T[n, 16 grp .. 16 grp + 15] of the tile at q from accumulator slot (tt & 1) -> red.add into G_S[k, n]: for
-    // a fixed k the 32 lanes hit one 128-byte line
+    // G_S^T[n, KQ grp .. KQ grp + KQ - 1] of the tile at q (tile index tt) -> red.add into G_S[k, n]: for a fixed k the
+    // 32 lanes hit one 128-byte line
     auto flush_gs = [&](const TilePos& q, uint32_t tt) {
-      const uint32_t slot = tt & 1;
-      mbar_wait(bar(B_GS_FULL + slot), (tt >> 1) & 1);
+      const uint32_t gslot = KH == 1 ? (tt & 1) : 0u, guse = KH == 1 ? (tt >> 1) : tt;
+      mbar_wait(bar(B_GS_FULL + gslot), guse & 1);
+      if (!want_gs) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + gslot));
+        return;
+      }
       tc_fence_after();
-      uint32_t v[16];
-      tmem_ld16(lane_addr + TM_GS + slot * 64 + grp * 16, v);
+      uint32_t v[KQ];
+#pragma unroll
+      for (int h = 0; h < KH; ++h) tmem_ld16(lane_addr + TM_GS + gslot * 64 + grp * KQ + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + slot));   // values are in registers: the accumulator is free
+      if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + gslot));   // values are in registers: the accumulator is free
       if (ABL(32)) return;
       const int n = q.st * TILE_N + row;
-      float* dst = p.GS + (size_t)(grp * 16) * N + n;
+      float* dst = p.GS + (size_t)(grp * KQ) * N + n;
       const uint32_t pitch = (uint32_t)N * 4u;
       const uint64_t a0 = reinterpret_cast<uint64_t>(dst);
       uint32_t lo = (uint32_t)a0;
       const uint32_t hi = (uint32_t)(a0 >> 32);
-      if (K == KP && (q.st + 1) * TILE_N <= N && pitch <= (1u << 26) && __all_sync(0xffffffffu, lo <= 0xffffffffu - 16u * pitch)) {
+      if (K == KPT && (q.st + 1) * TILE_N <= N && pitch <= (1u << 26) &&
+          __all_sync(0xffffffffu, lo <= 0xffffffffu - (uint32_t)KQ * pitch)) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < KQ; ++k) {
           red_add_f32_lohi(lo, hi, __uint_as_float(v[k]));
           lo += pitch;
         }
       } else if (n < N) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (grp * 16 + k < K) red_add_f32(dst + (size_t)k * N, __uint_as_float(v[k]));
+        for (int k = 0; k < KQ; ++k)
+          if (grp * KQ + k < K) red_add_f32(dst + (size_t)k * N, __uint_as_float(v[k]));
       }
     };
-    // G_A[m, 16 grp .. 16 grp + 15] = hh + hl halves of the row segment of m-block q.mb
+    // G_A[m, KQ grp .. KQ grp + KQ - 1] of the row segment of m-block q.mb (KH = 1: hh + hl halves)
     auto flush_ga = [&](const TilePos& q, uint32_t seg) {
       mbar_wait(bar(B_GA_FULL), seg & 1);
+      if (!want_ga) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
+        return;
+      }
       tc_fence_after();
-      uint32_t v[16], w[16];
-      tmem_ld16(lane_addr + TM_GA + grp * 16, v);
-      tmem_ld16(lane_addr + TM_GA + 64 + grp * 16, w);
-      tmem_ld_wait();
+      float s[KQ];
+      if constexpr (KH == 1) {
+        uint32_t v[16], w[16];
+        tmem_ld16(lane_addr + TM_GA + grp * 16, v);
+        tmem_ld16(lane_addr + TM_GA + 64 + grp * 16, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s[k] = __uint_as_float(v[k]) + __uint_as_float(w[k]);
+      } else {
+        uint32_t v[KQ];
+#pragma unroll
+        for (int h = 0; h < KH; ++h) tmem_ld16(lane_addr + TM_GA + grp * KQ + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) s[k] = __uint_as_float(v[k]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_GA_EMPTY));
       const int m = q.mb * TILE_M + row;
       if (m < M) {
-        float* dst = GA + (size_t)m * K + grp * 16;
-        float s[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) s[k] = __uint_as_float(v[k]) + __uint_as_float(w[k]);
+        float* dst = GA + (size_t)m * K + grp * KQ;
         if ((K & 3) == 0) {
 #pragma unroll
-          for (int k = 0; k < 16; k += 4)
-            if (grp * 16 + k < K) red_add_v4(dst + k, s[k], s[k + 1], s[k + 2], s[k + 3]);
+          for (int k = 0; k < KQ; k += 4)
+            if (grp * KQ + k < K) red_add_v4(dst + k, s[k], s[k + 1], s[k + 2], s[k + 3]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (grp * 16 + k < K) red_add_f32(dst + k, s[k]);
+          for (int k = 0; k < KQ; ++k)
+            if (grp * KQ + k < K) red_add_f32(dst + k, s[k]);
         }
       }
     };
@@ -605,6 +742,11 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     if (ntiles > 0) issue_y(pos);
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t slot = t & 1;
+      // KH = 2: the G_S^T accumulator is single-buffered, so the previous tile's flush has to leave tensor memory
+      // before this tile's R^T hand-off lets issuer 2 overwrite it
+      if constexpr (KH == 2) {
+        if (t > 0) flush_gs(prev, t - 1);
+      }
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
       tc_fence_after();
       if (warp == 4) TR(3, t, 0);
@@ -642,15 +784,17 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       // ---- R^T from registers to shared memory (the MN-major operand of the G_A GEMM) once MMA3(t-1) released it
       mbar_wait(bar(B_RS_EMPTY), (t & 1) ^ 1);
       if (warp == 4) TR(3, t, 2);
+      if (want_ga) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (ABL(16)) continue;
-        const int chunk = ((grp & 1) * 4 + c) ^ (row & 7);
-        const int o = (c >> 1) * 16 + (c & 1) * 4;     // hi pairs of elements 8c .. 8c+7
-        *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hl[o], hl[o + 1], hl[o + 2], hl[o + 3]);
-        *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(hl[o + 8], hl[o + 9], hl[o + 10], hl[o + 11]);
+        for (int c = 0; c < 4; ++c) {
+          if (ABL(16)) continue;
+          const int chunk = ((grp & 1) * 4 + c) ^ (row & 7);
+          const int o = (c >> 1) * 16 + (c & 1) * 4;     // hi pairs of elements 8c .. 8c+7
+          *reinterpret_cast<uint4*>(rh + (chunk << 4)) = make_uint4(hl[o], hl[o + 1], hl[o + 2], hl[o + 3]);
+          *reinterpret_cast<uint4*>(rl + (chunk << 4)) = make_uint4(hl[o + 8], hl[o + 9], hl[o + 10], hl[o + 11]);
+        }
+        fence_async_smem();   // generic-proxy writes of R^T -> visible to the tensor-core (async) proxy
       }
-      fence_async_smem();   // generic-proxy writes of R^T -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(B_RS_FULL));             // MMA3(t) may start
@@ -664,7 +808,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       if (t + 1 < ntiles) issue_y(nxt);
       // ---- gradient flushes, one tile behind so that they never wait for the tensor pipe in steady state
       if (t > 0) {
-        flush_gs(prev, t - 1);
+        if constexpr (KH == 1) flush_gs(prev, t - 1);
         if (prev_last) {
           flush_ga(prev, seg);
           ++seg;
@@ -735,13 +879,14 @@ int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const voi
 
 struct UmmaPlan {
   int M, N, K, Mp, Np;
+  int KH, KPT;   // k-halves (1: K <= 64, 2: K <= 128) and the padded K = 64 KH of the bf16 operand buffers
   const float* Y;
   int ldY;
   void *Ahi, *Alo, *Shi, *Slo;  // bf16 operand buffers (zero padded)
   CUtensorMap tmAhi, tmAlo, tmShi, tmSlo;
 };
 
-bool umma_supported(int M, int N, int K) { return K >= 1 && K <= KP && M >= 1 && N >= 1; }
+bool umma_supported(int M, int N, int K) { return K >= 1 && K <= 2 * KP && M >= 1 && N >= 1; }
 
 int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out) {
   PMX_REQUIRE(umma_supported(M, N, K), "unsupported shape for the tcgen05 kernel");
@@ -752,25 +897,34 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   pl->Y = Y; pl->ldY = ldY;
   pl->Mp = pmx_div_up(M, TILE_M) * TILE_M;
   pl->Np = pmx_div_up(N, TILE_N) * TILE_N;
+  pl->KH = K <= KP ? 1 : 2;
+  pl->KPT = KP * pl->KH;
+  const int KPT = pl->KPT;
   PMX_CUDA(cudaSetDevice(ctx->device));
-  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Ahi, (size_t)pl->Mp * KP * 2));
-  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Alo, (size_t)pl->Mp * KP * 2));
-  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Shi, (size_t)KP * pl->Np * 2));
-  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Slo, (size_t)KP * pl->Np * 2));
-  PMX_CUDA(cudaMemsetAsync(pl->Ahi, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
-  PMX_CUDA(cudaMemsetAsync(pl->Alo, 0, (size_t)pl->Mp * KP * 2, ctx->stream));
-  PMX_CUDA(cudaMemsetAsync(pl->Shi, 0, (size_t)KP * pl->Np * 2, ctx->stream));
-  PMX_CUDA(cudaMemsetAsync(pl->Slo, 0, (size_t)KP * pl->Np * 2, ctx->stream));
-  PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, KP, (uint64_t)pl->Mp, KP * 2, KP, TILE_M));
-  PMX_CHECK(make_map(&pl->tmAlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Alo, KP, (uint64_t)pl->Mp, KP * 2, KP, TILE_M));
-  PMX_CHECK(make_map(&pl->tmShi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Shi, (uint64_t)pl->Np, KP, (uint64_t)pl->Np * 2, 64, KP));
-  PMX_CHECK(make_map(&pl->tmSlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Slo, (uint64_t)pl->Np, KP, (uint64_t)pl->Np * 2, 64, KP));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Ahi, (size_t)pl->Mp * KPT * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Alo, (size_t)pl->Mp * KPT * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Shi, (size_t)KPT * pl->Np * 2));
+  PMX_CHECK(pmx_dev_alloc(ctx, &pl->Slo, (size_t)KPT * pl->Np * 2));
+  PMX_CUDA(cudaMemsetAsync(pl->Ahi, 0, (size_t)pl->Mp * KPT * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Alo, 0, (size_t)pl->Mp * KPT * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Shi, 0, (size_t)KPT * pl->Np * 2, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(pl->Slo, 0, (size_t)KPT * pl->Np * 2, ctx->stream));
+  // boxes: A = 64 k-columns x 128 m-rows at (64 kh, m0); S = 64 n-columns x 64 k-rows at (n0, 64 kh)
+  PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, KPT, (uint64_t)pl->Mp, KPT * 2, KP, TILE_M));
+  PMX_CHECK(make_map(&pl->tmAlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Alo, KPT, (uint64_t)pl->Mp, KPT * 2, KP, TILE_M));
+  PMX_CHECK(make_map(&pl->tmShi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Shi, (uint64_t)pl->Np, KPT, (uint64_t)pl->Np * 2, 64, KP));
+  PMX_CHECK(make_map(&pl->tmSlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Slo, (uint64_t)pl->Np, KPT, (uint64_t)pl->Np * 2, 64, KP));
   static bool attr = false;
   if (!attr) {
-    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int s1 = (int)SmemMap<1>::BYTES, s2 = (int)SmemMap<2>::BYTES;
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     attr = true;
   }
   *out = pl;
@@ -786,25 +940,28 @@ void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* pl) {
   delete pl;
 }
 
-void umma_plan_buffers(UmmaPlan* pl, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldS) {
-  *Ahi = pl->Ahi; *Alo = pl->Alo; *Shi = pl->Shi; *Slo = pl->Slo; *ldS = pl->Np;
+void umma_plan_buffers(UmmaPlan* pl, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldA, int* ldS) {
+  *Ahi = pl->Ahi; *Alo = pl->Alo; *Shi = pl->Shi; *Slo = pl->Slo; *ldA = pl->KPT; *ldS = pl->Np;
 }
 
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done, int skip_split, const unsigned* ga_epoch, size_t ga_stride) {
+                     const int* done, int skip_split, const unsigned* ga_epoch, size_t ga_stride, int want) {
+  const bool want_ga = (want & 1) && GA, want_gs = (want & 2) && GS;
   if (!skip_split) {
-    PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, KP, done));
-    PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, KP, pl->Np, done));
+    PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, pl->KPT, done));
+    PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, pl->KPT, pl->Np, done));
   }
   // (with ga_epoch the G_A pair lives in the peer arena and is cleared by the consumer of the previous epoch)
-  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, (size_t)pl->K * pl->N, GA, ga_epoch ? 0 : (size_t)pl->M * pl->K,
-                         reinterpret_cast<float*>(loss), loss ? 2 : 0, done));
+  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, want_gs ? (size_t)pl->K * pl->N : 0, GA,
+                         (ga_epoch || !want_ga) ? 0 : (size_t)pl->M * pl->K, reinterpret_cast<float*>(loss), loss ? 2 : 0,
+                         done));
   Params p;
   p.M = pl->M; p.N = pl->N; p.K = pl->K;
   p.NS = pl->Np / TILE_N;
   p.total_tiles = (long long)(pl->Mp / TILE_M) * p.NS;
   p.Y = pl->Y; p.ldY = pl->ldY;
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
+  p.want_ga = want_ga ? 1 : 0; p.want_gs = want_gs ? 1 : 0;
   p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride;
   {
     const char* ab = getenv("PMX_ABLATE");
@@ -821,11 +978,18 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;
   if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
   {
-    // four instantiations: with / without the loss reduction, production / debug (timing ablations + trace)
+    // instantiations: k-halves (K <= 64 / K <= 128) x with / without the loss reduction x production / debug
+    // (timing ablations + trace)
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
-    auto kern = dbg ? (loss ? k_grad_umma<true, true> : k_grad_umma<false, true>)
-                    : (loss ? k_grad_umma<true, false> : k_grad_umma<false, false>);
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+    if (pl->KH == 1) {
+      auto kern = dbg ? (loss ? k_grad_umma<1, true, true> : k_grad_umma<1, false, true>)
+                      : (loss ? k_grad_umma<1, true, false> : k_grad_umma<1, false, false>);
+      kern<<<grid, NUM_THREADS, SmemMap<1>::BYTES, ctx->stream>>>(pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+    } else {
+      auto kern = dbg ? (loss ? k_grad_umma<2, true, true> : k_grad_umma<2, false, true>)
+                      : (loss ? k_grad_umma<2, true, false> : k_grad_umma<2, false, false>);
+      kern<<<grid, NUM_THREADS, SmemMap<2>::BYTES, ctx->stream>>>(pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);
+    }
   }
   if (prof) {
     PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream));

@@ -4,7 +4,8 @@
 
 struct UmmaPlan;
 
-// shapes the tcgen05 kernel takes: K <= 64 (operands are zero-padded to K = 64), any M, any N
+// shapes the tcgen05 kernel takes: K <= 128 (operands are zero-padded to K = 64 or, for K > 64, to 128 and handled
+// as two 64-deep k-halves), any M, any N
 bool umma_supported(int M, int N, int K);
 // Y: fp32 with a row pitch of ldY floats (any alignment: the kernel reads it with plain coalesced loads)
 int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out);
@@ -13,7 +14,11 @@ void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // kernels wrote them -- so the two split passes are skipped
 // ga_epoch != nullptr (sharded runs over peer memory): GA is the base of a pair of buffers ga_stride elements apart
 // and the partials go to buffer (*ga_epoch + 1) & 1, which its consumer cleared (comm.cu)
+// want: bit 0 = G_A, bit 1 = G_S; a gradient that is not wanted costs no MMAs, no flush and its buffer is not
+// touched (bsdmm needs one gradient per pass, nmf.py:181-185; the loss needs none, nmf.py:13-25)
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* plan, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done, int skip_split = 0, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0);
-// bf16 operand buffers of the plan: A_hi/A_lo are Mp x 64 (row pitch 64), S_hi/S_lo are 64 x Np (row pitch *ldS)
-void umma_plan_buffers(UmmaPlan* plan, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldS);
+                     const int* done, int skip_split = 0, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0,
+                     int want = 3);
+// bf16 operand buffers of the plan: A_hi/A_lo are Mp x *ldA (row pitch *ldA = padded K), S_hi/S_lo are *ldA x Np
+// (row pitch *ldS)
+void umma_plan_buffers(UmmaPlan* plan, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldA, int* ldS);

@@ -99,8 +99,10 @@ int pull_ctl(pmx_nmf* h) {
 // gradient at (A, S) into (GA, GS) [+ loss], kernel selection, multi-GPU sum of the G_A partials
 // defer_reduce: the caller sums the G_A partials over the ranks itself (PGM does it on the side stream)
 // ga_epoch: peer-memory mode of the tcgen05 kernel (GA = base of the buffer pair in the arena, no reduction here)
+// want: bit 0 = G_A, bit 1 = G_S (tcgen05 kernel only: an unwanted gradient costs no MMAs and no flush)
 int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* GS, double* loss, int kernel,
-                 const int* done, bool defer_reduce = false, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0) {
+                 const int* done, bool defer_reduce = false, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0,
+                 int want = 3) {
   pmx_ctx* ctx = h->ctx;
   bool use_umma = false;
   if (kernel == 2) use_umma = true;
@@ -112,14 +114,14 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
     }
     if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
     const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
-    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride));
+    PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride, want));
     h->used_umma = true;
   } else {
     h->used_umma = false;
     PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, A, S, h->M, h->N, h->K, GA, GS, loss, done));
   }
   if (ctx->world > 1) {
-    if (!defer_reduce) PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
+    if (!defer_reduce && (want & 1) && GA) PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
     if (loss) PMX_CHECK(pmx_comm_allreduce_internal(ctx, loss, 1, 1, ctx->stream));
   }
   return PMX_OK;
@@ -312,14 +314,21 @@ int pmx_nmf_device_ptr(pmx_nmf* h, int which, float** dev_ptr) {
 
 int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
   PMX_REQUIRE(h && loss_host, "NULL argument");
-  // scratch gradients: the loss is a by-product of the residual pass
-  float *ga, *gs;
-  PMX_CHECK(alloc_f(h->ctx, &ga, (size_t)h->M * h->K));
-  PMX_CHECK(alloc_f(h->ctx, &gs, (size_t)h->K * h->N));
-  int st = nmf_gradient(h, h->A, h->S, ga, gs, &h->ctl->norms[6], 0, nullptr);
-  if (st == PMX_OK) st = pull_ctl(h);
-  pmx_dev_free(h->ctx, ga);
-  pmx_dev_free(h->ctx, gs);
+  // the loss is a by-product of the residual pass: the tcgen05 kernel runs it alone (no gradient GEMMs, no flush,
+  // no scratch); the SIMT kernel (tiny problems) still produces both gradients into scratch buffers
+  int st;
+  if (nmf_uses_umma(h, 0)) {
+    st = nmf_gradient(h, h->A, h->S, nullptr, nullptr, &h->ctl->norms[6], 0, nullptr, false, nullptr, 0, 0);
+    if (st == PMX_OK) st = pull_ctl(h);
+  } else {
+    float *ga, *gs;
+    PMX_CHECK(alloc_f(h->ctx, &ga, (size_t)h->M * h->K));
+    PMX_CHECK(alloc_f(h->ctx, &gs, (size_t)h->K * h->N));
+    st = nmf_gradient(h, h->A, h->S, ga, gs, &h->ctl->norms[6], 0, nullptr);
+    if (st == PMX_OK) st = pull_ctl(h);
+    pmx_dev_free(h->ctx, ga);
+    pmx_dev_free(h->ctx, gs);
+  }
   *loss_host = h->h_ctl->norms[6];
   return st;
 }
@@ -439,12 +448,12 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   // when the tcgen05 kernel is in use (and the next gradient is taken at (A, S) itself, i.e. no extrapolation) the
   // update kernels also write the bf16 (hi, lo) operands of the next iteration's GEMMs
   void *Ahi = nullptr, *Alo = nullptr, *Shi = nullptr, *Slo = nullptr;
-  int ldS = 0;
+  int ldA = 64, ldS = 0;
   const bool fuse_split = h->used_umma && h->plan && !h->pgm.accelerated;
-  if (fuse_split) umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldS);
+  if (fuse_split) umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldA, &ldS);
   io.Xin = Ae; io.G = h->GA; io.Xprev = h->A; io.Xout = h->A; io.Xold_out = h->A_old;
   io.norms = &h->ctl->norms[0]; io.rows = h->M; io.cols = h->K; io.step.ptr = &h->ctl->step[0];
-  io.hi = (unsigned short*)Ahi; io.lo = (unsigned short*)Alo; io.ld_split = 64;
+  io.hi = (unsigned short*)Ahi; io.lo = (unsigned short*)Alo; io.ld_split = ldA;
   {  // the two block updates are independent (Jacobi, algorithms.py:105-108): A on the side stream, S on the main one
     PMX_CUDA(cudaEventRecord(ctx->ev_fork2, ctx->stream));
     PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
@@ -769,14 +778,16 @@ int pmx_nmf_bsdmm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int*
   for (int i = 0; i < n_iter; ++i) {
     if (h->h_ctl->done) break;
     // block A (Gauss-Seidel: uses the current S), then block S with the updated A  (algorithms.py:805-839)
+    // (the reference's closure evaluates BOTH gradients per block and keeps one, nmf.py:181-185: 12 MNK flop per outer
+    // iteration; the tcgen05 kernel skips the unused GEMM and its flush: 8 MNK)
     PMX_CHECK(nmf_steps(h, h->A, h->S, true, false));
-    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
+    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done, false, nullptr, 0, 1));
     PMX_CHECK(nmf_steps_join(h));
     PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 0, h->A, h->GA, h->Zg[0], h->Ug[0], h->Z0, sums, h->M, h->K, o.n_g_A, dA,
                                  gA, &h->ctl->step[0], h->bs_norms, o.e_rel_A, o.e_abs_A, false,
                                  (double)h->M * h->K));
     PMX_CHECK(nmf_steps(h, h->A, h->S, false, true));
-    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));
+    PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done, false, nullptr, 0, 2));
     PMX_CHECK(nmf_steps_join(h));
     PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 1, h->S, h->GS, h->Zg[1], h->Ug[1], h->Z0, sums, h->K, h->N, o.n_g_S, dS,
                                  gS, &h->ctl->step[1], h->bs_norms + 32, o.e_rel_S, o.e_abs_S, true,
@@ -802,7 +813,7 @@ int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, i
   bool use_umma = (kernel == 2) || (kernel == 0 && umma_supported(M, N, K) && (long long)M * N >= 128LL * 128);
   if (use_umma) {
     if (!umma_supported(M, N, K)) {
-      pmx_set_error("tcgen05 gradient kernel needs K <= 64 (M=%d N=%d K=%d)", M, N, K);
+      pmx_set_error("tcgen05 gradient kernel needs K <= 128 (M=%d N=%d K=%d)", M, N, K);
       return PMX_ERR_UNSUPPORTED;
     }
     UmmaPlan* plan = nullptr;
