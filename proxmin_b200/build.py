@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libproxmin_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "comm.cu", "elementwise.cu", "gram.cu", "grad_simt.cu", "grad_umma.cu", "nmf_solver.cu", "admm.cu", "solver_kernels.cu", "ew.cu"]
+SOURCES = ["api.cu", "comm.cu", "elementwise.cu", "gram.cu", "grad_simt.cu", "grad_umma.cu", "nmf_solver.cu", "admm.cu", "solver_kernels.cu", "ew.cu", "pgm_tail.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -50,7 +50,11 @@ struct pmx_ctl {
   float step[2];     // 1/lambda_max for A and S (algorithms.py:106)
   float lip[2];      // lambda_max(S S^T), lambda_max(A^T A)
   float psi_max[2];  // adaprox: max(Psi) per block (algorithms.py:384)
-  float pad[2];
+  float step2[2][2]; // fused PGM tail: steps double-buffered by iteration parity ([it & 1] = steps of iteration `it`)
+  int fault;         // a peer did not answer within the spin limit (multi-GPU exchange): the solve is aborted
+  unsigned par_ctr;  // fused PGM tail: iterations whose factor updates are complete (parity of the gradient buffers)
+  int final_pending; // fused PGM tail: the roles kernel finished an iteration that k_tail_final has not closed yet
+  int pad;
 };
 
 // ---- peer-memory exchange (comm.cu): symmetric device regions mapped into every rank of the box over CUDA IPC

@@ -257,8 +257,10 @@ struct Params {
   const float* Y;         // fp32, row pitch ldY floats
   int ldY;
   float* GA;
-  const unsigned* ga_epoch;   // sharded runs: G_A partials go to buffer parity (*ga_epoch + 1) & 1 of a pair, see comm.cu
-  long long ga_stride;        // elements between the two buffers
+  const unsigned* ga_epoch;   // parity counter: the gradients go to buffer (*ga_epoch + 1) & 1 of a pair (sharded runs: the
+                              // peer epoch of comm.cu; fused PGM tail: the iteration counter, see pgm_tail.cu)
+  long long ga_stride;        // elements between the two G_A buffers
+  long long gs_stride;        // elements between the two G_S buffers (0: G_S is a single buffer)
   float* GS;
   double* loss;
   const int* done;
@@ -621,7 +623,9 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     const uint64_t pol = ABL(128) ? l2_policy_normal() : l2_policy_evict_first();
     const int K = p.K, N = p.N, M = p.M, ldY = p.ldY;
     constexpr int KQ = 16 * KH;              // gradient columns (k) this warp flushes: [grp * KQ, grp * KQ + KQ)
-    float* const GA = p.ga_epoch ? p.GA + (size_t)((*p.ga_epoch + 1u) & 1u) * p.ga_stride : p.GA;
+    const unsigned parity = p.ga_epoch ? ((*p.ga_epoch + 1u) & 1u) : 0u;
+    float* const GA = p.GA + (size_t)parity * p.ga_stride;
+    float* const GSb = p.GS + (size_t)parity * p.gs_stride;
     // shared-memory destinations of this thread's R^T chunk (row n, 128B-swizzled 16-byte chunks): loop invariant
     uint8_t* const rh = base_ptr + OFF_R_HI + (grp >> 1) * PANEL_R + row * 128;
     uint8_t* const rl = base_ptr + OFF_R_LO + (grp >> 1) * PANEL_R + row * 128;
@@ -676,7 +680,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + gslot));   // values are in registers: the accumulator is free
       if (ABL(32)) return;
       const int n = q.st * TILE_N + row;
-      float* dst = p.GS + (size_t)(grp * KQ) * N + n;
+      float* dst = GSb + (size_t)(grp * KQ) * N + n;
       const uint32_t pitch = (uint32_t)N * 4u;
       const uint64_t a0 = reinterpret_cast<uint64_t>(dst);
       uint32_t lo = (uint32_t)a0;
@@ -742,11 +746,6 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     if (ntiles > 0) issue_y(pos);
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t slot = t & 1;
-      // KH = 2: the G_S^T accumulator is single-buffered, so the previous tile's flush has to leave tensor memory
-      // before this tile's R^T hand-off lets issuer 2 overwrite it
-      if constexpr (KH == 2) {
-        if (t > 0) flush_gs(prev, t - 1);
-      }
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
       tc_fence_after();
       if (warp == 4) TR(3, t, 0);
@@ -781,6 +780,12 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_RT_FULL + slot));       // MMA2(t) may start
       if (warp == 4) TR(3, t, 1);
+      // KH = 2: the G_S^T accumulator is single-buffered: issuer 2 may only start on this tile once the previous tile's
+      // G_S^T has left tensor memory.  Flushing it here -- after this tile's conversion, which therefore overlaps the
+      // G_S MMAs of the previous tile -- keeps the serial chain per tile at (G_S MMAs + one TMEM read).
+      if constexpr (KH == 2) {
+        if (t > 0) flush_gs(prev, t - 1);
+      }
       // ---- R^T from registers to shared memory (the MN-major operand of the G_A GEMM) once MMA3(t-1) released it
       mbar_wait(bar(B_RS_EMPTY), (t & 1) ^ 1);
       if (warp == 4) TR(3, t, 2);
@@ -882,7 +887,8 @@ struct UmmaPlan {
   int KH, KPT;   // k-halves (1: K <= 64, 2: K <= 128) and the padded K = 64 KH of the bf16 operand buffers
   const float* Y;
   int ldY;
-  void *Ahi, *Alo, *Shi, *Slo;  // bf16 operand buffers (zero padded)
+  void *Ahi, *Alo, *Shi, *Slo;  // bf16 operand buffers (zero padded) the kernel reads
+  void *Ahi_own, *Alo_own;      // the plan's own A buffers (Ahi/Alo may point at external ones, umma_plan_use_A)
   CUtensorMap tmAhi, tmAlo, tmShi, tmSlo;
 };
 
@@ -905,6 +911,8 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   PMX_CHECK(pmx_dev_alloc(ctx, &pl->Alo, (size_t)pl->Mp * KPT * 2));
   PMX_CHECK(pmx_dev_alloc(ctx, &pl->Shi, (size_t)KPT * pl->Np * 2));
   PMX_CHECK(pmx_dev_alloc(ctx, &pl->Slo, (size_t)KPT * pl->Np * 2));
+  pl->Ahi_own = pl->Ahi;
+  pl->Alo_own = pl->Alo;
   PMX_CUDA(cudaMemsetAsync(pl->Ahi, 0, (size_t)pl->Mp * KPT * 2, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(pl->Alo, 0, (size_t)pl->Mp * KPT * 2, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(pl->Shi, 0, (size_t)KPT * pl->Np * 2, ctx->stream));
@@ -931,10 +939,18 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
   return PMX_OK;
 }
 
+int umma_plan_use_A(UmmaPlan* pl, void* Ahi, void* Alo) {
+  pl->Ahi = Ahi ? Ahi : pl->Ahi_own;
+  pl->Alo = Alo ? Alo : pl->Alo_own;
+  PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, pl->KPT, (uint64_t)pl->Mp, pl->KPT * 2, KP, TILE_M));
+  PMX_CHECK(make_map(&pl->tmAlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Alo, pl->KPT, (uint64_t)pl->Mp, pl->KPT * 2, KP, TILE_M));
+  return PMX_OK;
+}
+
 void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* pl) {
   if (!pl) return;
-  pmx_dev_free(ctx, pl->Ahi);
-  pmx_dev_free(ctx, pl->Alo);
+  pmx_dev_free(ctx, pl->Ahi_own);
+  pmx_dev_free(ctx, pl->Alo_own);
   pmx_dev_free(ctx, pl->Shi);
   pmx_dev_free(ctx, pl->Slo);
   delete pl;
@@ -945,14 +961,16 @@ void umma_plan_buffers(UmmaPlan* pl, void** Ahi, void** Alo, void** Shi, void** 
 }
 
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S, float* GA, float* GS, double* loss,
-                     const int* done, int skip_split, const unsigned* ga_epoch, size_t ga_stride, int want) {
+                     const int* done, int skip_split, const unsigned* ga_epoch, size_t ga_stride, int want,
+                     size_t gs_stride, int reserve_sms) {
   const bool want_ga = (want & 1) && GA, want_gs = (want & 2) && GS;
   if (!skip_split) {
     PMX_CHECK(launch_split_bf16(ctx, A, pl->M, pl->K, pl->Ahi, pl->Alo, pl->Mp, pl->KPT, done));
     PMX_CHECK(launch_split_bf16(ctx, S, pl->K, pl->N, pl->Shi, pl->Slo, pl->KPT, pl->Np, done));
   }
   // (with ga_epoch the G_A pair lives in the peer arena and is cleared by the consumer of the previous epoch)
-  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, want_gs ? (size_t)pl->K * pl->N : 0, GA,
+  // (with gs_stride the G_S pair is cleared by the fused tail of the previous iteration as well)
+  PMX_CHECK(launch_zero3(ctx, ctx->stream, GS, (want_gs && gs_stride == 0) ? (size_t)pl->K * pl->N : 0, GA,
                          (ga_epoch || !want_ga) ? 0 : (size_t)pl->M * pl->K, reinterpret_cast<float*>(loss), loss ? 2 : 0,
                          done));
   Params p;
@@ -962,7 +980,7 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   p.Y = pl->Y; p.ldY = pl->ldY;
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
   p.want_ga = want_ga ? 1 : 0; p.want_gs = want_gs ? 1 : 0;
-  p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride;
+  p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride; p.gs_stride = (long long)gs_stride;
   {
     const char* ab = getenv("PMX_ABLATE");
     p.ablate = ab ? atoi(ab) : 0;
@@ -974,7 +992,10 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
       p.trace = d_trace;
     }
   }
-  int grid = (int)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
+  // reserve_sms: SMs left free for a small kernel that runs next to this one on another stream (the persistent CTAs
+  // own their SM: 190+ KB of shared memory each)
+  const int sms = ctx->sm_count - reserve_sms > 0 ? ctx->sm_count - reserve_sms : 1;
+  int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;
   if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
   {

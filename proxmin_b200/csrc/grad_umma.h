@@ -18,7 +18,10 @@ void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // touched (bsdmm needs one gradient per pass, nmf.py:181-185; the loss needs none, nmf.py:13-25)
 int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* plan, const float* A, const float* S, float* GA, float* GS, double* loss,
                      const int* done, int skip_split = 0, const unsigned* ga_epoch = nullptr, size_t ga_stride = 0,
-                     int want = 3);
+                     int want = 3, size_t gs_stride = 0, int reserve_sms = 0);
+// the A operand buffers the kernel reads (tensor maps re-encoded): external Mp x ldA bf16 buffers, e.g. regions of the
+// peer arena that every rank's fused PGM tail writes into; nullptr = back to the plan's own buffers
+int umma_plan_use_A(UmmaPlan* plan, void* Ahi, void* Alo);
 // bf16 operand buffers of the plan: A_hi/A_lo are Mp x *ldA (row pitch *ldA = padded K), S_hi/S_lo are *ldA x Np
 // (row pitch *ldS)
 void umma_plan_buffers(UmmaPlan* plan, void** Ahi, void** Alo, void** Shi, void** Slo, int* ldA, int* ldS);

@@ -3,12 +3,11 @@
 //
 //   k_gram<TALL>   : Gram += X^T X (tall M x K operand) or X X^T (wide K x N operand), fp32 tiles in
 //                    shared memory, 4x4 register blocks, persistent blocks, one fp64 atomic flush per block.
-//   k_lambda_max   : one CTA per Gram: repeated squaring (B <- B^2 / trace) drives B to v1 v1^T for any
-//                    spectral gap, two fp64 power steps and a Rayleigh quotient with the ORIGINAL Gram give
-//                    lambda_max to ~1e-7 relative -- the accuracy LAPACK geev gives the reference in fp32.
-//                    Writes lip / step = 1/lip into the control block; flags non-finite input
-//                    (reference: numpy.linalg.LinAlgError from eigvals, utils.py:34).
+//   k_lambda_max   : one 256-thread CTA per Gram (algorithm in lambda_max.cuh: repeated squaring + fp64 power steps
+//                    + Rayleigh quotient, ~1e-7 relative).  Writes lip / step = 1/lip into the control block; flags
+//                    non-finite input (reference: numpy.linalg.LinAlgError from eigvals, utils.py:34).
 #include "common.cuh"
+#include "lambda_max.cuh"
 
 int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done);
 int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nblocks, int C, double* gram, const int* done);
@@ -115,155 +114,28 @@ __global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ p
   if (b1 > b0) atomicAdd(&gram[e], ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
 }
 
-// One CTA (1024 threads).  gram: C x C fp64 (symmetric PSD).  which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].
+// One CTA per Gram matrix (gridDim.x = 1 or 2): 256 threads for C <= 64, 1024 above (the squarings are C^3 FMAs).  gram: C x C fp64 (symmetric PSD).
+// which: 0 -> lip[0]/step[0], 1 -> lip[1]/step[1].  The algorithm lives in lambda_max.cuh (shared with the fused PGM
+// tail); 36 KB of shared memory for C = 64.
 __global__ void __launch_bounds__(1024) k_lambda_max(const double* __restrict__ gram0, int which0,
-                                                     const double* __restrict__ gram1, int which1, int C,
-                                                     pmx_ctl* ctl, int squarings) {
+                                                    const double* __restrict__ gram1, int which1, int C,
+                                                    pmx_ctl* ctl, int squarings) {
   if (ctl->done) return;
-  // one CTA per Gram matrix (gridDim.x = 1 or 2)
   const double* __restrict__ gram = blockIdx.x == 0 ? gram0 : gram1;
   const int which = blockIdx.x == 0 ? which0 : which1;
-  extern __shared__ __align__(16) float smem[];
-  const int C4 = (C + 3) & ~3;
-  const int ldt = C4 + 4;
-  float* B0 = smem;                        // [C4][ldt]
-  float* B1 = B0 + (size_t)C4 * ldt;       // [C4][ldt]
-  double* v = reinterpret_cast<double*>(B1 + (size_t)C4 * ldt);  // [C4]
-  double* w = v + C4;                                             // [C4]
-  __shared__ double s_red[32];
-  __shared__ double s_scalar;
-  __shared__ int s_bad;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_bad = 0;
-  __syncthreads();
-
-  // load, detect non-finite entries, trace
-  double tr = 0.0;
-  for (int idx = tid; idx < C4 * C4; idx += blockDim.x) {
-    const int i = idx / C4, j = idx - i * C4;
-    double g = (i < C && j < C) ? gram[(size_t)i * C + j] : 0.0;
-    if (!isfinite(g)) s_bad = 1;
-    if (i == j) tr += g;
-    B0[i * ldt + j] = (float)g;
-  }
-  // block sum of tr
-  for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
-  if ((tid & 31) == 0) s_red[tid >> 5] = tr;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
-    s_scalar = t;
-  }
-  __syncthreads();
-  const double trace0 = s_scalar;
-  if (s_bad || !isfinite(trace0)) {
-    if (tid == 0) {
-      ctl->nonfinite = 1;
-      ctl->done = 1;
-      ctl->lip[which] = __int_as_float(0x7fc00000);
-      ctl->step[which] = __int_as_float(0x7fc00000);
-    }
-    return;
-  }
-  if (trace0 <= 0.0) {  // zero matrix: lambda_max = 0, step = 1/0 = inf (the reference divides by zero too)
-    if (tid == 0) {
-      ctl->lip[which] = 0.f;
-      ctl->step[which] = __int_as_float(0x7f800000);
-    }
-    return;
-  }
-  // normalise by the trace so every power keeps entries in (0, 1]
-  {
-    const float inv = (float)(1.0 / trace0);
-    for (int idx = tid; idx < C4 * ldt; idx += blockDim.x) B0[idx] *= inv;
-  }
-  __syncthreads();
-
-  const int nt = C4 / 4;
-  const int ntiles = nt * nt;
-  float* cur = B0;
-  float* nxt = B1;
-  for (int s = 0; s < squarings; ++s) {
-    // nxt = cur^T cur = cur^2 (symmetric)
-    float tr_part = 0.f;
-    for (int tile = tid; tile < ntiles; tile += blockDim.x) {
-      const int i0 = (tile / nt) * 4, j0 = (tile % nt) * 4;
-      float acc[4][4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
-      gram_block(cur, C4, ldt, i0, j0, acc);
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          nxt[(i0 + p) * ldt + j0 + q] = acc[p][q];
-          if (i0 + p == j0 + q) tr_part += acc[p][q];
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) tr_part += __shfl_xor_sync(0xffffffffu, tr_part, o);
-    __syncthreads();  // everybody finished reading cur / s_red from the previous round
-    if ((tid & 31) == 0) s_red[tid >> 5] = (double)tr_part;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0;
-      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
-      s_scalar = t;
-    }
-    __syncthreads();
-    // tr(B^2) with tr(B) = 1 equals sum_i w_i^2 of the normalised spectrum: it reaches 1 when the power is
-    // rank one to fp32 resolution -- no further squaring can change the selected column
-    const bool rank_one = (1.0 - s_scalar) < 2e-6;
-    const float inv = (float)(1.0 / s_scalar);
-    for (int idx = tid; idx < C4 * ldt; idx += blockDim.x) nxt[idx] *= inv;
-    __syncthreads();
-    float* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
-    if (rank_one) break;   // block-uniform (s_scalar is shared)
-  }
-  // v = column of the (near rank-one) power with the largest diagonal entry
-  if (tid == 0) {
-    int best = 0;
-    float bd = -1.f;
-    for (int i = 0; i < C; ++i)
-      if (cur[i * ldt + i] > bd) {
-        bd = cur[i * ldt + i];
-        best = i;
-      }
-    s_bad = best;
-  }
-  __syncthreads();
-  const int col = s_bad;
-  for (int i = tid; i < C4; i += blockDim.x) v[i] = (i < C) ? (double)cur[i * ldt + col] : 0.0;
-  __syncthreads();
-  // two fp64 power steps with the original Gram, then the Rayleigh quotient
-  for (int rep = 0; rep < 3; ++rep) {
-    for (int i = tid; i < C; i += blockDim.x) {
-      double acc = 0.0;
-      for (int j = 0; j < C; ++j) acc += gram[(size_t)i * C + j] * v[j];
-      w[i] = acc;
-    }
-    __syncthreads();
-    if (rep == 2) break;
-    if (tid == 0) {
-      double nn = 0;
-      for (int i = 0; i < C; ++i) nn += w[i] * w[i];
-      s_scalar = nn > 0 ? 1.0 / sqrt(nn) : 0.0;
-    }
-    __syncthreads();
-    for (int i = tid; i < C; i += blockDim.x) v[i] = w[i] * s_scalar;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    double num = 0, den = 0;
-    for (int i = 0; i < C; ++i) {
-      num += v[i] * w[i];
-      den += v[i] * v[i];
-    }
-    const double lam = den > 0 ? num / den : 0.0;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  int status = 0;
+  const double lam = lmax::block_lambda_max(gram, C, lm_smem, squarings, &status, lmax::whole_block());
+  if (threadIdx.x != 0) return;
+  if (status == 1) {        // reference: numpy.linalg.LinAlgError from eigvals (utils.py:34)
+    ctl->nonfinite = 1;
+    ctl->done = 1;
+    ctl->lip[which] = __int_as_float(0x7fc00000);
+    ctl->step[which] = __int_as_float(0x7fc00000);
+  } else if (status == 2) {  // zero matrix: lambda_max = 0, step = 1/0 = inf (the reference divides by zero too)
+    ctl->lip[which] = 0.f;
+    ctl->step[which] = __int_as_float(0x7f800000);
+  } else {
     const float lf = (float)lam;             // the reference's eigvals runs in fp32 for fp32 inputs
     ctl->lip[which] = lf;
     ctl->step[which] = 1.0f / lf;            // nmf.py:45,49
@@ -327,8 +199,7 @@ int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int w
     pmx_set_error("Gram dimension K=%d exceeds the supported maximum %d", C, kMaxK);
     return PMX_ERR_UNSUPPORTED;
   }
-  const int C4 = (C + 3) & ~3;
-  const size_t smem = 2 * (size_t)C4 * (C4 + 4) * sizeof(float) + 2 * (size_t)C4 * sizeof(double);
+  const size_t smem = lmax::smem_bytes(C);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_lambda_max, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -338,7 +209,7 @@ int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int w
     }
     attr_set = true;
   }
-  k_lambda_max<<<gram1 ? 2 : 1, 1024, smem, st>>>(gram0, which0, gram1, which1, C, ctl, 20);
+  k_lambda_max<<<gram1 ? 2 : 1, C <= 64 ? 256 : 1024, smem, st>>>(gram0, which0, gram1, which1, C, ctl, 20);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_lambda_max");
 }

@@ -12,6 +12,7 @@
 
 #include "kernels.h"
 #include "grad_umma.h"
+#include "pgm_tail.h"
 
 int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
 bool pmx_comm_has_aux(pmx_ctx* ctx);
@@ -47,6 +48,18 @@ struct pmx_nmf {
   size_t peer_off_gram;        // arena offset of the (Gram(S), norms) pair
   cudaGraphExec_t pgm_graph;   // steady-state iteration captured once, replayed per iteration (no launch gaps)
   long long pgm_graph_launches; // kernels inside the graph (for the launch counter)
+  // ---- fused PGM tail (pgm_tail.cu): iteration = gradient kernel -> [peer signal] -> one tail kernel
+  bool tail_mode;              // this PGM solve runs the fused tail
+  bool tail_ready;             // steps / bf16 operands / arena copies match the current (A, S)
+  float *GA2, *GS2;            // gradient buffer pairs indexed by the iteration parity (GA2: single-GPU runs only;
+                               // sharded runs keep the G_A pair in the peer arena)
+  size_t ga_stride, gs_stride; // elements between the two buffers of a pair
+  float* tail_gram_rep;        // [2][PMX_TAIL_NREP][K*K] replicated Gram accumulators
+  double* tail_acc;            // [2][4] norm partials
+  unsigned* tail_tickets;      // [4]
+  size_t off_GA, off_A, off_Ahi, off_Alo, off_inbox;   // regions of the peer arena (bytes)
+  cudaGraphExec_t tail_graph;
+  long long tail_graph_launches;
   // ---- adaprox
   pmx_adaprox_opts ada;
   float *MA, *MS, *VA, *VS, *VhA, *VhS, *Psi, *Z0, *Z1, *alphaA, *alphaS;
@@ -251,6 +264,12 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaFree(h->ctl);
   cudaFreeHost(h->h_ctl);
   if (h->pgm_graph) cudaGraphExecDestroy(h->pgm_graph);
+  if (h->tail_graph) cudaGraphExecDestroy(h->tail_graph);
+  if (h->GA2) pmx_dev_free(h->ctx, h->GA2);
+  if (h->GS2) pmx_dev_free(h->ctx, h->GS2);
+  if (h->tail_gram_rep) cudaFree(h->tail_gram_rep);
+  if (h->tail_acc) cudaFree(h->tail_acc);
+  if (h->tail_tickets) cudaFree(h->tail_tickets);
   if (h->plan) umma_plan_destroy(h->ctx, h->plan);
   delete h;
   return PMX_OK;
@@ -294,7 +313,8 @@ int pmx_nmf_set(pmx_nmf* h, int which, const float* host_src) {
   if (which == PMX_A || which == PMX_S) {
     h->split_valid = false;
     h->gramS_valid = false;
-  h->gram_pending = false;
+    h->gram_pending = false;
+    h->tail_ready = false;
   }
   return pmx_h2d(h->ctx, p, host_src, n * sizeof(float));
 }
@@ -365,6 +385,180 @@ struct StageTimer {
 };
 static StageTimer g_stage;
 
+// ------------------------------------------------------------------ fused PGM tail: host side
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// decides whether this PGM solve takes the fused tail (pgm_tail.cu) and sets up its buffers
+static int tail_setup(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  h->tail_mode = false;
+  h->tail_ready = false;
+  if (h->tail_graph) {
+    cudaGraphExecDestroy(h->tail_graph);
+    h->tail_graph = nullptr;
+  }
+  if (h->plan) PMX_CHECK(umma_plan_use_A(h->plan, nullptr, nullptr));
+  const int axA = chain_unity_axis(h->chA), axS = chain_unity_axis(h->chS);
+  const bool ok = !getenv("PMX_NO_FUSED_TAIL") && !h->pgm.accelerated && nmf_uses_umma(h, h->pgm.kernel) && h->K <= 64 &&
+                  axA == -1 && (axS == -1 || axS == 0) && (ctx->world == 1 || pmx_peer_available(ctx)) &&
+                  h->M >= ctx->world;
+  if (!ok) return PMX_OK;
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N, kk = (size_t)h->K * h->K;
+  h->ga_stride = (mk + 63) & ~(size_t)63;
+  h->gs_stride = (kn + 63) & ~(size_t)63;
+  if (ctx->world > 1) {
+    const size_t Mp = (size_t)pmx_div_up(h->M, 128) * 128;
+    h->off_GA = 0;
+    h->off_A = align256(h->off_GA + 2 * h->ga_stride * sizeof(float));
+    h->off_Ahi = align256(h->off_A + mk * sizeof(float));
+    h->off_Alo = align256(h->off_Ahi + Mp * 64 * 2);
+    h->off_inbox = align256(h->off_Alo + Mp * 64 * 2);
+    const size_t total = h->off_inbox + sizeof(double) * (kk + 4) * PMX_MAX_WORLD * 4;
+    pmx_peer_region* ar = nullptr;
+    if (pmx_peer_arena(ctx, total, &ar) != PMX_OK) return PMX_OK;   // no symmetric memory: the NCCL path takes over
+    PMX_CHECK(pmx_peer_reset(ctx));
+  } else {
+    if (!h->GA2) PMX_CHECK(alloc_f(ctx, &h->GA2, 2 * h->ga_stride));
+    PMX_CUDA(cudaMemsetAsync(h->GA2, 0, sizeof(float) * 2 * h->ga_stride, ctx->stream));
+  }
+  if (!h->GS2) PMX_CHECK(alloc_f(ctx, &h->GS2, 2 * h->gs_stride));
+  PMX_CUDA(cudaMemsetAsync(h->GS2, 0, sizeof(float) * 2 * h->gs_stride, ctx->stream));
+  if (!h->tail_gram_rep) PMX_CUDA(cudaMalloc((void**)&h->tail_gram_rep, sizeof(float) * 2 * PMX_TAIL_NREP * kk));
+  if (!h->tail_acc) PMX_CUDA(cudaMalloc((void**)&h->tail_acc, sizeof(double) * 8));
+  if (!h->tail_tickets) PMX_CUDA(cudaMalloc((void**)&h->tail_tickets, sizeof(unsigned) * 4));
+  PMX_CUDA(cudaMemsetAsync(h->tail_gram_rep, 0, sizeof(float) * 2 * PMX_TAIL_NREP * kk, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->tail_acc, 0, sizeof(double) * 8, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->tail_tickets, 0, sizeof(unsigned) * 4, ctx->stream));
+  h->tail_mode = true;
+  return PMX_OK;
+}
+
+static float* tail_ga_base(pmx_nmf* h) {
+  return h->ctx->world > 1 ? reinterpret_cast<float*>(static_cast<char*>(h->ctx->peer_arena.local) + h->off_GA) : h->GA2;
+}
+
+// before the first fused iteration (and after the host replaced A or S): bf16 operands, arena copies of A, and the
+// steps of the coming iteration from the stand-alone Gram / lambda_max kernels (nmf.py:44-49)
+static int tail_prologue(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  const int* done = &h->ctl->done;
+  if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
+  if (ctx->world > 1) {
+    char* loc = static_cast<char*>(ctx->peer_arena.local);
+    PMX_CHECK(umma_plan_use_A(h->plan, loc + h->off_Ahi, loc + h->off_Alo));
+    PMX_CUDA(cudaMemcpyAsync(loc + h->off_A, h->A, sizeof(float) * (size_t)h->M * h->K, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    PMX_CHECK(umma_plan_use_A(h->plan, nullptr, nullptr));
+  }
+  void *Ahi, *Alo, *Shi, *Slo;
+  int ldA, ldS;
+  umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldA, &ldS);
+  const int Mp = pmx_div_up(h->M, 128) * 128;
+  PMX_CHECK(launch_split_bf16(ctx, h->A, h->M, h->K, Ahi, Alo, Mp, ldA, done));
+  PMX_CHECK(launch_split_bf16(ctx, h->S, h->K, h->N, Shi, Slo, ldA, ldS, done));
+  h->gramS_valid = false;
+  h->gram_pending = false;
+  PMX_CHECK(nmf_steps(h, h->A, h->S, true, true));
+  PMX_CHECK(nmf_steps_join(h));
+  PMX_CHECK(launch_tail_seed_steps(ctx, h->ctl));
+  h->split_valid = true;
+  h->used_umma = true;
+  h->tail_ready = true;
+  return PMX_OK;
+}
+
+// argument block of the two tail kernels (fixed for a solve: the kernels replay inside the iteration's CUDA graph)
+static int tail_args(pmx_nmf* h, PgmTailArgs* out) {
+  pmx_ctx* ctx = h->ctx;
+  PgmTailArgs& a = *out;
+  memset(&a, 0, sizeof(a));
+  a.M = h->M; a.N = h->N; a.K = h->K;
+  a.world = ctx->world; a.rank = ctx->rank;
+  a.ctl = h->ctl;
+  void *Ahi, *Alo, *Shi, *Slo;
+  int ldA, ldS;
+  umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldA, &ldS);
+  a.S = h->S; a.GS2 = h->GS2; a.gs_stride = (long long)h->gs_stride;
+  a.Shi = (unsigned short*)Shi; a.Slo = (unsigned short*)Slo; a.ldS = ldS;
+  a.chS = h->chS;
+  a.nS = pgm_tail_s_blocks(ctx, h->N, &a.n_tiles_S);
+  // rows of A this rank updates (reduce-scatter slice): an even split of the M rows, PMX_TAIL_RA rows per block
+  a.m_lo = (int)((long long)h->M * ctx->rank / ctx->world);
+  a.m_hi = (int)((long long)h->M * (ctx->rank + 1) / ctx->world);
+  a.nA = pmx_div_up(a.m_hi - a.m_lo, PMX_TAIL_RA);
+  a.chA = h->chA;
+  a.ldA = ldA;
+  a.ga_stride = (long long)h->ga_stride;
+  a.A_loc = h->A; a.GA2_loc = h->GA2; a.Ahi_loc = (unsigned short*)Ahi; a.Alo_loc = (unsigned short*)Alo;
+  if (ctx->world > 1) {
+    for (int r = 0; r < PMX_MAX_WORLD; ++r) {
+      a.arena.p[r] = ctx->peer_arena.peer[r];
+      a.flags.p[r] = ctx->peer_flags.peer[r];
+    }
+    a.off_GA = h->off_GA; a.off_A = h->off_A; a.off_Ahi = h->off_Ahi; a.off_Alo = h->off_Alo; a.off_inbox = h->off_inbox;
+    a.epoch = ctx->peer_epoch;
+    a.my_flags = reinterpret_cast<const unsigned*>(ctx->peer_flags.local);
+  }
+  a.gram_rep = h->tail_gram_rep; a.acc = h->tail_acc; a.tickets = h->tail_tickets;
+  const float eA = h->pgm.e_rel_A, eS = h->pgm.e_rel_S;
+  a.e2A = (float)((double)eA * (double)eA);
+  a.e2S = (float)((double)eS * (double)eS);
+  if (a.nA < 1) {   // more ranks than rows of A: not a shape the fused tail is meant for
+    pmx_set_error("fused PGM tail: M = %d is too small for %d ranks", h->M, ctx->world);
+    return PMX_ERR_UNSUPPORTED;
+  }
+  return PMX_OK;
+}
+
+// One iteration:   side stream: k_tail_final of the PREVIOUS iteration (Gram totals, lambda_max -> the steps this
+//                               iteration's tail uses, convergence test) -- next to the gradient kernel, which leaves
+//                               it one SM
+//                  main stream: gradient kernel -> [peer signal] -> (join) -> k_pgm_tail
+static int tail_enqueue_iteration(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  const int* done = &h->ctl->done;
+  PgmTailArgs a;
+  PMX_CHECK(tail_args(h, &a));
+  PMX_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+  PMX_CHECK(launch_tail_final(ctx, ctx->aux, a));
+  PMX_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
+  PMX_CHECK(launch_grad_umma(ctx, h->plan, h->A, h->S, tail_ga_base(h), h->GS2, nullptr, done, 1, &h->ctl->par_ctr,
+                             h->ga_stride, 3, h->gs_stride, /*reserve_sms=*/1));
+  // the signal is unconditional (no `done` test): the stop flag may be raised by the concurrent k_tail_final while
+  // this stream passes here, and the epoch counters of the ranks must stay in lockstep
+  if (ctx->world > 1) PMX_CHECK(pmx_peer_signal(ctx, 0, ctx->stream, nullptr, nullptr, 0, 0));
+  PMX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  PMX_CHECK(launch_pgm_tail(ctx, a));
+  h->it_enqueued += 1;
+  return PMX_OK;
+}
+
+// closes the last enqueued iteration (no-op when nothing is pending): before the host looks at the control block
+static int tail_close(pmx_nmf* h) {
+  PgmTailArgs a;
+  PMX_CHECK(tail_args(h, &a));
+  return launch_tail_final(h->ctx, h->ctx->stream, a);
+}
+
+// after a run: the last gradients (algorithms.py:144 hands them back) and, sharded, the replicated A leave the
+// parity / arena buffers for the plain ones that pmx_nmf_get and the other solvers read
+static int tail_publish(pmx_nmf* h) {
+  pmx_ctx* ctx = h->ctx;
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  const size_t par = (size_t)(h->h_ctl->it & 1);
+  if (h->h_ctl->it > 0) {
+    PMX_CUDA(cudaMemcpyAsync(h->GS, h->GS2 + par * h->gs_stride, sizeof(float) * kn, cudaMemcpyDeviceToDevice, ctx->stream));
+    PMX_CUDA(cudaMemcpyAsync(h->GA, tail_ga_base(h) + par * h->ga_stride, sizeof(float) * mk, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->GA, mk, 0, ctx->stream));
+  }
+  if (ctx->world > 1 && h->tail_ready)
+    PMX_CUDA(cudaMemcpyAsync(h->A, static_cast<char*>(ctx->peer_arena.local) + h->off_A, sizeof(float) * mk,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMX_OK;
+}
+
 // ------------------------------------------------------------------ PGM
 int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
@@ -387,9 +581,10 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
     if (!h->Se) PMX_CHECK(alloc_f(h->ctx, &h->Se, (size_t)h->K * h->N));
   }
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  PMX_CHECK(tail_setup(h));
   // sharded run over peer memory (comm.cu): [G_A partials x 2 | (Gram(S) partial, 3 norms, pad) x 2] in the arena
   h->peer_mode = false;
-  if (pmx_peer_available(h->ctx) && nmf_uses_umma(h, h->pgm.kernel) && umma_supported(h->M, h->N, h->K) &&
+  if (!h->tail_mode && pmx_peer_available(h->ctx) && nmf_uses_umma(h, h->pgm.kernel) && umma_supported(h->M, h->N, h->K) &&
       !getenv("PMX_NO_PEER_PGM")) {
     const size_t mk = (size_t)h->M * h->K, kk4 = (size_t)h->K * h->K + 4;
     h->peer_off_gram = (2 * mk * sizeof(float) + 255) & ~(size_t)255;
@@ -524,6 +719,46 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
   const int it0 = h->h_ctl->it;
   bool stopped = h->h_ctl->done != 0;
   static const bool no_graph = getenv("PMX_NO_GRAPH") != nullptr;
+  if (h->tail_mode) {
+    // fused tail: gradient kernel -> [peer signal] -> tail kernel on one stream, replayed as a CUDA graph
+    if (!h->tail_ready && n_iter > 0 && !stopped) PMX_CHECK(tail_prologue(h));
+    for (int i = 0; i < n_iter && !stopped; ++i) {
+      static const bool tail_trace = getenv("PMX_TAIL_TRACE") != nullptr;
+      if (!no_graph && !h->ctx->profile && !tail_trace) {
+        if (!h->tail_graph) {
+          cudaGraph_t graph = nullptr;
+          const long long l0 = h->ctx->launches;
+          PMX_CUDA(cudaStreamBeginCapture(h->ctx->stream, cudaStreamCaptureModeThreadLocal));
+          int st = tail_enqueue_iteration(h);
+          cudaError_t ce = cudaStreamEndCapture(h->ctx->stream, &graph);
+          h->it_enqueued -= 1;               // the capture did not execute anything
+          h->tail_graph_launches = h->ctx->launches - l0;
+          h->ctx->launches = l0;
+          if (st != PMX_OK) return st;
+          if (ce != cudaSuccess || !graph) {
+            pmx_set_error("CUDA graph capture of the PGM iteration failed: %s", cudaGetErrorString(ce));
+            return PMX_ERR_CUDA;
+          }
+          PMX_CUDA(cudaGraphInstantiate(&h->tail_graph, graph, nullptr, nullptr, 0));
+          cudaGraphDestroy(graph);
+        }
+        PMX_CUDA(cudaGraphLaunch(h->tail_graph, h->ctx->stream));
+        h->ctx->launches += h->tail_graph_launches;
+        h->it_enqueued += 1;
+      } else {
+        PMX_CHECK(tail_enqueue_iteration(h));
+      }
+      if ((i + 1) % h->pgm.check_every == 0 && i + 1 < n_iter) {
+        PMX_CHECK(tail_close(h));
+        PMX_CHECK(pull_ctl(h));
+        stopped = h->h_ctl->done != 0;
+      }
+    }
+    if (h->tail_ready) PMX_CHECK(tail_close(h));
+    PMX_CHECK(pull_ctl(h));
+    PMX_CHECK(tail_publish(h));
+    n_iter = 0;   // (skips the unfused loop below; the common epilogue reports the results)
+  }
   for (int i = 0; i < n_iter && !stopped; ++i) {
     // Steady state (tcgen05 kernel, operands split by the update kernels, no extrapolation, no per-launch
     // profiling): the iteration is a fixed kernel sequence on two streams (+ NCCL) -> replay it as a CUDA graph.
@@ -564,6 +799,10 @@ int pmx_nmf_pgm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int* c
   if (conv_S) *conv_S = h->h_ctl->conv[1];
   if (step_A) *step_A = h->h_ctl->step[0];
   if (step_S) *step_S = h->h_ctl->step[1];
+  if (h->h_ctl->fault) {
+    pmx_set_error("multi-GPU exchange timed out: a peer did not reach iteration %d", h->h_ctl->it);
+    return PMX_ERR_NCCL;
+  }
   if (h->h_ctl->nonfinite) {
     pmx_set_error("Gram matrix contains infs or NaNs (iteration %d)", h->h_ctl->it);
     return PMX_ERR_NONFINITE;
@@ -576,6 +815,8 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   PMX_REQUIRE(h && opts, "NULL argument");
   PMX_REQUIRE(opts->scheme >= PMX_ADAM && opts->scheme <= PMX_RADAM, "unknown adaprox scheme");
   h->ada = *opts;
+  h->tail_mode = false;
+  if (h->plan) PMX_CHECK(umma_plan_use_A(h->plan, nullptr, nullptr));
   h->split_valid = false;
   h->gramS_valid = false;
   h->gram_pending = false;
@@ -737,6 +978,8 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
         }
   PMX_CHECK(reject_sharded_row_unity(h, make_chain(&opts->prox_S), "bsdmm (direct prox_S)"));
   h->bs = *opts;
+  h->tail_mode = false;
+  if (h->plan) PMX_CHECK(umma_plan_use_A(h->plan, nullptr, nullptr));
   h->split_valid = false;
   h->gramS_valid = false;
   h->gram_pending = false;
