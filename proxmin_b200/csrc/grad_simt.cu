@@ -4,6 +4,7 @@
 // 64 x 64 tile of Y: the residual tile never leaves shared memory, so Y is read exactly once and
 // no M x N temporary exists (the reference materialises three of them, nmf.py:40).
 #include "common.cuh"
+#include "grad_umma.h"
 
 int launch_zero(pmx_ctx* ctx, cudaStream_t st, float* p, size_t n, const int* done);
 
@@ -12,7 +13,7 @@ namespace {
 constexpr int BM = 64, BN = 64;
 constexpr int LDR = BN + 1;  // residual tile row stride (odd: conflict-free row-strided reads)
 
-__global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, int ldY, const float* __restrict__ A,
+__global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, int ldY, int y_blocked, const float* __restrict__ A,
                                                    const float* __restrict__ S, int M, int N, int K,
                                                    float* __restrict__ GA, float* __restrict__ GS,
                                                    double* __restrict__ loss, const int* done) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, 
       for (int q = 0; q < 4; ++q) {
         const int m = m_base + m0 + p, n = n_base + n0 + q;
         float d = 0.f;
-        if (m < M && n < N) d = r[p][q] - Y[(size_t)m * ldY + n];  // nmf.py:40 (W == 1)
+        if (m < M && n < N) d = r[p][q] - Y[pmx_y_index(m, n, ldY, y_blocked)];  // nmf.py:40 (W == 1)
         sR[(m0 + p) * LDR + n0 + q] = d;
         loss_part = fmaf(d, d, loss_part);
       }
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, 
 }  // namespace
 
 // G_A, G_S (and *loss) must be zeroed by the caller-facing wrapper: done here on the same stream.
-int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, const float* S, int M, int N, int K, float* GA,
+int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done) {
   if (K > 128) {
     pmx_set_error("SIMT gradient kernel supports K <= 128 (got %d)", K);
@@ -132,7 +133,31 @@ int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, cons
   const long long ntiles = (long long)pmx_div_up(M, BM) * pmx_div_up(N, BN);
   long long blocks = ntiles < (long long)ctx->sm_count * 4 ? ntiles : (long long)ctx->sm_count * 4;
   if (blocks < 1) return PMX_OK;
-  k_grad_simt<<<(int)blocks, 256, smem, ctx->stream>>>(Y, ldY, A, S, M, N, K, GA, GS, loss, done);
+  k_grad_simt<<<(int)blocks, 256, smem, ctx->stream>>>(Y, ldY, y_blocked, A, S, M, N, K, GA, GS, loss, done);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_grad_simt");
+}
+
+// ---------------------------------------------------------------- row-major staging buffer -> tiled Y (pmx_nmf_set_Y)
+namespace {
+__global__ void __launch_bounds__(256) k_y_interleave(const float* __restrict__ stage, int pitch, int nrows, int ncols,
+                                                      float* __restrict__ Yb, int ldY, int m0, int col0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.y;                     // row quad inside the chunk
+  if (n >= ncols) return;
+  float v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) v[r] = 4 * q + r < nrows ? __ldcs(stage + (size_t)(4 * q + r) * pitch + n) : 0.f;
+  float4* dst = reinterpret_cast<float4*>(Yb + pmx_y_index(m0 + 4 * q, col0 + n, ldY, 1));
+  *dst = make_float4(v[0], v[1], v[2], v[3]);
+}
+}  // namespace
+
+int launch_y_interleave(pmx_ctx* ctx, cudaStream_t st, const float* stage, int pitch, int nrows, int ncols, float* Yb, int ldY,
+                        int m0, int col0) {
+  if (nrows <= 0 || ncols <= 0) return PMX_OK;
+  dim3 grid((unsigned)pmx_div_up(ncols, 256), (unsigned)pmx_div_up(nrows, 4));
+  k_y_interleave<<<grid, 256, 0, st>>>(stage, pitch, nrows, ncols, Yb, ldY, m0, col0);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_y_interleave");
 }

@@ -54,6 +54,21 @@
 
 namespace {
 
+#ifndef PMX_REG_DEC
+#define PMX_REG_DEC 32     // registers per thread of the producer / issuer warps after setmaxnreg.dec
+#endif
+#ifndef PMX_REG_INC
+#define PMX_REG_INC 112    // registers per thread of the residual warps after setmaxnreg.inc
+#endif
+#define PMX_STR2(x) #x
+#define PMX_STR(x) PMX_STR2(x)
+#ifndef PMX_WAIT_HINT_NS
+#define PMX_WAIT_HINT_NS 0   // suspend-time hint (ns) of the mbarrier waits; 0 = plain try_wait loop.  Round 2: every
+                            // hint (100 ns .. 10 ms) costs 6 % -- the wake-up of a suspended warp sits in the tile chain
+#endif
+#ifndef PMX_GS_STACK
+#define PMX_GS_STACK 0
+#endif
 constexpr int TILE_M = 128, TILE_N = 128, KP = 64;
 constexpr int S_SLOTS = 3;          // S-tile ring
 constexpr uint32_t PANEL_S = 64 * 128;    // bytes of one S panel (64 k-rows)
@@ -92,9 +107,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// (the suspend-time hint lets the hardware park the waiting warp instead of re-issuing the probe: 20 warps spin on
-// barriers most of the time and every probe costs an issue slot)
+// (round 1 passed a suspend-time hint so that parked warps do not burn issue slots; with the leaner round-2 instruction
+// stream every hint value from 100 ns to 10 ms measured 6 % SLOWER than the plain try_wait loop, and non-blocking
+// test_wait spin loops for the issuers / the accumulator wait changed nothing: profiles/README.md)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if PMX_WAIT_HINT_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -102,8 +119,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar),
-      "r"(parity), "r"(0x989680u)
+      "r"(parity), "r"((uint32_t)PMX_WAIT_HINT_NS)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(
@@ -191,6 +219,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -217,6 +251,13 @@ __device__ __forceinline__ float ld_stream_lohi(uint32_t lo, uint32_t hi, uint64
       "ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [a], %3;\n\t}"
       : "=f"(v)
       : "r"(lo), "r"(hi), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_v4(const float* ptr, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(policy));
   return v;
 }
 __device__ __forceinline__ void red_add_f32_lohi(uint32_t lo, uint32_t hi, float v) {
@@ -264,6 +305,7 @@ struct Params {
   float* GS;
   double* loss;
   const int* done;
+  int y_blocked;          // layout of Y: 0 row-major (pitch ldY), 1 tiled (see grad_umma.h)
   int want_ga, want_gs;   // 0: that gradient GEMM and its flush are skipped (bsdmm needs one gradient per pass, the loss none)
   long long* trace;       // debug: clock64 timeline of CTA 0 (env PMX_TRACE), [role][tile][event]
   int ablate;             // debug/timing only (env PMX_ABLATE): bit0 no MMA1, 1 no MMA2, 2 no MMA3, 3 no Y read, 4 no R store, 5 no G_S flush, 7 no L2 hint on the Y loads
@@ -313,6 +355,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
   if (p.done && *p.done) return;
   constexpr uint32_t OFF_R_HI = SmemMap<KH>::R_HI, OFF_R_LO = SmemMap<KH>::R_LO, OFF_BAR = SmemMap<KH>::BAR;
   constexpr int KPT = KP * KH;   // padded K
+  constexpr bool GS1 = (KH == 2) || PMX_GS_STACK;   // single-buffered 128-column G_S^T accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -367,12 +410,20 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
   auto a_hi = [&](int kh) { return base + OFF_A + (uint32_t)kh * PANEL_R; };
   auto a_lo = [&](int kh) { return base + OFF_A + (uint32_t)(KH + kh) * PANEL_R; };
 
+  // Register split (setmaxnreg, per warpgroup of 4 warps): the producer and the three issuer warps (warpgroup 0) need
+  // few registers, the residual warps hold three half-tile Y buffers + R^T + the accumulator chunk.  The kernel is
+  // compiled for 96 registers per thread (640 threads); warpgroup 0 drops to 32, warpgroups 1-4 rise to 112.  The
+  // increase is served ONLY from what the decrease released (128 x 64 = 8192 = 512 x 16 registers): a larger request
+  // blocks forever (launch_grad_umma checks the compiled register count against this budget).
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 " PMX_STR(PMX_REG_DEC) ";");
   if (warp == 0) {
     // ============================== TMA producer ==============================
     // S tiles (per tile) and A tiles (per row segment) into shared memory; Y is NOT staged in shared memory: the
     // residual warps read it from global memory (coalesced along n).
-    // (explicit L2 prefetches of Y -- TMA prefetch boxes or per-lane prefetch.global.L2, 1 to 8 tiles ahead -- were
-    // measured and only slowed the kernel down: the plain loads already keep HBM busy)
+    // (explicit L2 prefetches of Y -- TMA prefetch boxes with and without an evict_first hint, per-lane
+    // prefetch.global.L2, 1 to 8 tiles ahead -- were measured in both rounds and only slowed the kernel down,
+    // monotonically with the distance: profiles/README.md)
     uint32_t seg = 0;
     const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t slot = 0, use = 0;
@@ -498,11 +549,12 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     // (MN-major B operand) is read from shared memory.  KH = 1: N = 64, double-buffered accumulator; KH = 2: the two
     // k-halves of the A tile are one N = 128 operand (LBO = distance of the halves), single accumulator.
     constexpr uint32_t ID_GS = make_idesc(128, 64 * KH, 0, 1);
+    constexpr uint32_t ID_GS_STACK = make_idesc(128, 128, 0, 1);
     uint32_t seg_full = 0;
     TilePos pos = pos0;
     for (int t = 0; t < ntiles; ++t, pos.next(NS)) {
       const uint32_t slot = t & 1;
-      const uint32_t gslot = KH == 1 ? slot : 0u, guse = KH == 1 ? (uint32_t)(t >> 1) : (uint32_t)t;
+      const uint32_t gslot = GS1 ? 0u : slot, guse = GS1 ? (uint32_t)t : (uint32_t)(t >> 1);
       if (first_in_seg(t, pos)) {
         mbar_wait(bar(B_A_FULL), seg_full & 1);          // already complete (MMA1 consumed it): visibility only
         ++seg_full;
@@ -516,22 +568,39 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       const uint32_t r_off[3] = {0, 0, 8};               // R_hi, R_hi, R_lo pairs of a k-step's 16 columns
       const uint32_t a_src[3] = {a_hi(0), a_lo(0), a_hi(0)};
       if (want_gs) {
-#pragma unroll
-        for (int term = 0; term < 3; ++term)
+        if constexpr (KH == 1 && PMX_GS_STACK) {
+          // G_S^T[n, (hh | hl)] = R_hi^T [A_hi | A_lo]  (one N = 128 instruction per k-step: the hi and lo panels of the
+          // A tile are PANEL_R apart = the LBO), then G_S^T[n, hh] += R_lo^T A_hi (N = 64); the flush adds the halves
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             if (ABL(2)) continue;
-            const uint32_t at = racc + ks * 16 + r_off[term];
-            const uint64_t bd = make_desc(a_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major, 64-wide atoms PANEL_R apart
-            umma_ts_e(d, at, bd, ID_GS, (term | ks) ? 1u : 0u);
+            const uint64_t bd = make_desc(a_hi(0) + ks * 2048, PANEL_R, 1024);
+            umma_ts_e(d, racc + ks * 16, bd, ID_GS_STACK, ks ? 1u : 0u);
           }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ABL(2)) continue;
+            const uint64_t bd = make_desc(a_hi(0) + ks * 2048, PANEL_R, 1024);
+            umma_ts_e(d, racc + ks * 16 + 8, bd, ID_GS, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              if (ABL(2)) continue;
+              const uint32_t at = racc + ks * 16 + r_off[term];
+              const uint64_t bd = make_desc(a_src[term] + ks * 2048, PANEL_R, 1024);  // MN-major, 64-wide atoms PANEL_R apart
+              umma_ts_e(d, at, bd, ID_GS, (term | ks) ? 1u : 0u);
+            }
+        }
       }
       tc_commit_e(bar(B_GS_FULL + gslot));
       tc_commit_e(bar(B_ACC_EMPTY + slot));  // MMA1(t+2) may overwrite these columns once R^T(t) has been consumed
       TR(1, t, 3);
       if (last_in_seg(t, pos)) tc_commit_e(bar(B_A_EMPTY));
     }
-  } else if (warp == 3) {
+  } else {
     // ============================== MMA issuer 3: G_A GEMM ==============================
     // KH = 1: G_A[m, (hh|hl)] += R_hi [S_hi;S_lo]^T ; G_A[m, hh] += R_lo S_hi^T   (M = m, K = n: 8 k-steps).  R comes
     // from the shared-memory copy of R^T (MN-major A operand), the stacked S slot is the K-major B operand.
@@ -611,7 +680,9 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         ++seg;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " PMX_STR(PMX_REG_INC) ";");
     // ============================== residual + flush warps (16) ==============================
     // Warp (q4, grp): TMEM lane quarter q4 (the 32 columns n = 32 q4 + lane of the tile), 32-row chunk grp of the
     // accumulator columns.  Per tile: residual chunk -> R^T (TMEM, registers -> SMEM), then the flush of the previous
@@ -630,40 +701,64 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     uint8_t* const rh = base_ptr + OFF_R_HI + (grp >> 1) * PANEL_R + row * 128;
     uint8_t* const rl = base_ptr + OFF_R_LO + (grp >> 1) * PANEL_R + row * 128;
     float loss_part = 0.f;
-    float y[32];   // Y[m0 + 32 grp + j][n] of the next tile, loaded a tile period ahead
-    auto issue_y = [&](const TilePos& q) {
-      const int m0 = q.mb * TILE_M + grp * 32, n0 = q.st * TILE_N;
-      const float* src = p.Y + (size_t)m0 * ldY + (n0 + row);
-      const uint32_t pitch = (uint32_t)ldY * 4u;
+    // Y in registers: three buffers of 16 rows (half of this warp's 32-row chunk of a tile) that rotate so that the
+    // loads run one to two tile periods ahead of their use -- tile t reads its first half from buffer (2t) % 3 and its
+    // second half from buffer (2t + 1) % 3; once both are consumed they are refilled with the second half of tile
+    // t + 1 and the first half of tile t + 2.  With a single 32-row buffer the loads of tile t + 1 could only be issued
+    // after the conversion of tile t and were needed right after it: DRAM latency (~700 cycles) and the transfer time
+    // of 64 KB through the SM's L2 port (~800 cycles) sat in the residual warps' serial chain of every tile
+    // (profiles/README.md, round-2 ablations).  The buffer index must be a compile-time constant (registers), hence
+    // the tile loop below is unrolled three times.
+    float y[48];
+    auto issue_y_half = [&](auto BUF, const TilePos& q, int h) {
+      constexpr int B0 = 16 * decltype(BUF)::value;
       if (ABL(8)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = 0.f;
+        for (int j = 0; j < 16; ++j) y[B0 + j] = 0.f;
+        return;
+      }
+      if (p.y_blocked) {
+        // tiled Y (grad_umma.h): the 128 x 128 tile is one contiguous 64 KB block [32 row quads][128 columns][4 rows], so
+        // one 16-byte load per lane brings 4 consecutive rows of column n, a warp instruction covers 512 contiguous
+        // bytes, a CTA streams its tile range as one contiguous region (the tile sequence is the storage order) and
+        // there are no edge cases: the padding of the device copy is zero
+        // (timing ablation 64: every tile reads tile (0, 0): same instructions, L2 hits instead of DRAM)
+        const float* src4 = p.Y + ((size_t)(ABL(64) ? 0 : q.mb * NS + q.st) * (TILE_M * TILE_N) +
+                                   (size_t)(grp * 8 + h * 4) * (TILE_N * 4) + row * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = ld_stream_v4(src4 + i * (TILE_N * 4), pol);
+          y[B0 + 4 * i] = v.x; y[B0 + 4 * i + 1] = v.y; y[B0 + 4 * i + 2] = v.z; y[B0 + 4 * i + 3] = v.w;
+        }
+        return;
+      }
+      // row-major Y (pmx_nmf_grad on a caller's matrix): for a fixed row the 32 lanes read one 128-byte line
+      const int m0 = q.mb * TILE_M + grp * 32 + h * 16, n0 = q.st * TILE_N;
+      const float* src = p.Y + (size_t)m0 * ldY + (n0 + row);
+      const uint32_t pitch = (uint32_t)ldY * 4u;
+      const uint64_t a0 = reinterpret_cast<uint64_t>(src);
+      uint32_t lo = (uint32_t)a0;
+      const uint32_t hi = (uint32_t)(a0 >> 32);
+      const bool interior = (m0 + 16 <= M) && (n0 + TILE_N <= N);
+      if (interior && pitch <= (1u << 26) && __all_sync(0xffffffffu, lo <= 0xffffffffu - 16u * pitch)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          y[B0 + j] = ld_stream_lohi(lo, hi, pol);
+          lo += pitch;
+        }
       } else {
-        const uint64_t a0 = reinterpret_cast<uint64_t>(src);
-        uint32_t lo = (uint32_t)a0;
-        const uint32_t hi = (uint32_t)(a0 >> 32);
-        const bool interior = (m0 + 32 <= M) && (n0 + TILE_N <= N);
-        if (interior && pitch <= (1u << 26) && __all_sync(0xffffffffu, lo <= 0xffffffffu - 32u * pitch)) {
-          // for a fixed j the 32 lanes read one 128-byte line; one IADD + one LDG per element
+        const bool col_ok = n0 + row < N;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] = ld_stream_lohi(lo, hi, pol);
-            lo += pitch;
-          }
-        } else {
-          const bool col_ok = n0 + row < N;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] = 0.f;
-            if (col_ok && m0 + j < M) y[j] = ld_stream(src + (size_t)j * ldY, pol);
-          }
+        for (int j = 0; j < 16; ++j) {
+          y[B0 + j] = 0.f;
+          if (col_ok && m0 + j < M) y[B0 + j] = ld_stream(src + (size_t)j * ldY, pol);
         }
       }
     };
     // G_S^T[n, KQ grp .. KQ grp + KQ - 1] of the tile at q (tile index tt) -> red.add into G_S[k, n]: for a fixed k the
     // 32 lanes hit one 128-byte line
     auto flush_gs = [&](const TilePos& q, uint32_t tt) {
-      const uint32_t gslot = KH == 1 ? (tt & 1) : 0u, guse = KH == 1 ? (tt >> 1) : tt;
+      const uint32_t gslot = GS1 ? 0u : (tt & 1), guse = GS1 ? tt : (tt >> 1);
       mbar_wait(bar(B_GS_FULL + gslot), guse & 1);
       if (!want_gs) {
         __syncwarp();
@@ -672,9 +767,21 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       }
       tc_fence_after();
       uint32_t v[KQ];
+      if constexpr (KH == 1 && PMX_GS_STACK) {
+        tmem_ld16(lane_addr + TM_GS + grp * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
 #pragma unroll
-      for (int h = 0; h < KH; ++h) tmem_ld16(lane_addr + TM_GS + gslot * 64 + grp * KQ + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
-      tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {   // the hl half in two steps of 8 columns (register pressure: R^T is still live)
+          uint32_t w[8];
+          tmem_ld8(lane_addr + TM_GS + 64 + grp * 16 + h * 8, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[h * 8 + k] = __float_as_uint(__uint_as_float(v[h * 8 + k]) + __uint_as_float(w[k]));
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < KH; ++h) tmem_ld16(lane_addr + TM_GS + gslot * 64 + grp * KQ + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_GS_EMPTY + gslot));   // values are in registers: the accumulator is free
@@ -743,8 +850,21 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     uint32_t seg = 0;
     TilePos pos = pos0, prev = pos0;
     bool prev_last = false;
-    if (ntiles > 0) issue_y(pos);
-    for (int t = 0; t < ntiles; ++t) {
+    using IC0 = std::integral_constant<int, 0>;
+    using IC1 = std::integral_constant<int, 1>;
+    using IC2 = std::integral_constant<int, 2>;
+    if (ntiles > 0) {
+      issue_y_half(IC0{}, pos0, 0);
+      issue_y_half(IC1{}, pos0, 1);
+      if (ntiles > 1) {
+        TilePos q1 = pos0;
+        q1.next(NS);
+        issue_y_half(IC2{}, q1, 0);
+      }
+    }
+    // one tile; ROT = t % 3 selects the register buffers: first half in buffer YA, second half in buffer YB
+    auto tile_body = [&](auto ROT, const int t) {
+      constexpr int YA = (2 * decltype(ROT)::value) % 3, YB = (2 * decltype(ROT)::value + 1) % 3;
       const uint32_t slot = t & 1;
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
       tc_fence_after();
@@ -755,6 +875,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       uint32_t hl[32];
       TilePos nxt = pos;
       nxt.next(NS);
+      TilePos nxt2 = nxt;
+      nxt2.next(NS);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t acc[16];
@@ -762,8 +884,8 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float r0 = __uint_as_float(acc[j]) - y[h * 16 + j];          // nmf.py:40  (A S - Y)
-          const float r1 = __uint_as_float(acc[j + 1]) - y[h * 16 + j + 1];
+          const float r0 = __uint_as_float(acc[j]) - y[(h == 0 ? YA : YB) * 16 + j];          // nmf.py:40  (A S - Y)
+          const float r1 = __uint_as_float(acc[j + 1]) - y[(h == 0 ? YA : YB) * 16 + j + 1];
           if (LOSS) {
             loss_part = fmaf(r0, r0, loss_part);
             loss_part = fmaf(r1, r1, loss_part);
@@ -783,7 +905,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       // KH = 2: the G_S^T accumulator is single-buffered: issuer 2 may only start on this tile once the previous tile's
       // G_S^T has left tensor memory.  Flushing it here -- after this tile's conversion, which therefore overlaps the
       // G_S MMAs of the previous tile -- keeps the serial chain per tile at (G_S MMAs + one TMEM read).
-      if constexpr (KH == 2) {
+      if constexpr (GS1) {
         if (t > 0) flush_gs(prev, t - 1);
       }
       // ---- R^T from registers to shared memory (the MN-major operand of the G_A GEMM) once MMA3(t-1) released it
@@ -806,14 +928,15 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         mbar_arrive(bar(B_ACC_EMPTY + slot));    // our reads of this accumulator are done
       }
       if (warp == 4) TR(3, t, 3);
-      // the Y loads of the next tile, issued after the hand-offs above so that load-queue back pressure never delays
-      // the MMA issuers: 64 KB per SM in flight while the tensor pipe works on this tile
-      // (re-loading every Y register right after its use, to keep the loads in flight from draining, was measured
-      // 8 % slower: the load issue then sits on the path to the R^T hand-off)
-      if (t + 1 < ntiles) issue_y(nxt);
+      // both Y buffers of this tile are consumed: refill them (second half of tile t + 1, first half of tile t + 2).
+      // Issued after the hand-offs above so that load-queue back pressure never delays the MMA issuers
+      // (re-loading every Y register right after its use was measured 8 % slower in round 1: the load issue then
+      // sits on the path to the R^T hand-off)
+      if (t + 1 < ntiles) issue_y_half(std::integral_constant<int, YA>{}, nxt, 1);
+      if (t + 2 < ntiles) issue_y_half(std::integral_constant<int, YB>{}, nxt2, 0);
       // ---- gradient flushes, one tile behind so that they never wait for the tensor pipe in steady state
       if (t > 0) {
-        if constexpr (KH == 1) flush_gs(prev, t - 1);
+        if constexpr (!GS1) flush_gs(prev, t - 1);
         if (prev_last) {
           flush_ga(prev, seg);
           ++seg;
@@ -823,6 +946,11 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       prev = pos;
       prev_last = last_in_seg(t, pos);
       pos = nxt;
+    };
+    for (int t = 0; t < ntiles; t += 3) {
+      tile_body(IC0{}, t);
+      if (t + 1 < ntiles) tile_body(IC1{}, t + 1);
+      if (t + 2 < ntiles) tile_body(IC2{}, t + 2);
     }
     if (ntiles > 0) {
       flush_gs(prev, ntiles - 1);
@@ -860,7 +988,8 @@ EncodeTiledFn get_encode() {
 }
 
 int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows,
-             uint64_t pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
+             uint64_t pitch_bytes, uint32_t box_cols, uint32_t box_rows,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     pmx_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -872,7 +1001,7 @@ int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const voi
   cuuint32_t estr[2] = {1, 1};
   (void)elem_bytes;
   CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     pmx_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PMX_ERR_CUDA;
@@ -890,17 +1019,23 @@ struct UmmaPlan {
   void *Ahi, *Alo, *Shi, *Slo;  // bf16 operand buffers (zero padded) the kernel reads
   void *Ahi_own, *Alo_own;      // the plan's own A buffers (Ahi/Alo may point at external ones, umma_plan_use_A)
   CUtensorMap tmAhi, tmAlo, tmShi, tmSlo;
+  int y_blocked;
 };
 
 bool umma_supported(int M, int N, int K) { return K >= 1 && K <= 2 * KP && M >= 1 && N >= 1; }
 
-int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out) {
+int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out, int y_blocked) {
   PMX_REQUIRE(umma_supported(M, N, K), "unsupported shape for the tcgen05 kernel");
-  PMX_REQUIRE(ldY >= N && (long long)ldY * 4 < (1LL << 31), "Y row pitch must cover N and stay below 2 GiB");
+  if (y_blocked) {
+    PMX_REQUIRE(ldY == (N + TILE_N - 1) / TILE_N && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+                "tiled Y: ldY must be the number of 128-column tiles per row block and the base 16-byte aligned");
+  } else {
+    PMX_REQUIRE(ldY >= N && (long long)ldY * 4 < (1LL << 31), "Y row pitch must cover N and stay below 2 GiB");
+  }
   UmmaPlan* pl = new UmmaPlan();
   memset(pl, 0, sizeof(*pl));
   pl->M = M; pl->N = N; pl->K = K;
-  pl->Y = Y; pl->ldY = ldY;
+  pl->Y = Y; pl->ldY = ldY; pl->y_blocked = y_blocked;
   pl->Mp = pmx_div_up(M, TILE_M) * TILE_M;
   pl->Np = pmx_div_up(N, TILE_N) * TILE_N;
   pl->KH = K <= KP ? 1 : 2;
@@ -981,6 +1116,7 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
   p.want_ga = want_ga ? 1 : 0; p.want_gs = want_gs ? 1 : 0;
   p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride; p.gs_stride = (long long)gs_stride;
+  p.y_blocked = pl->y_blocked;
   {
     const char* ab = getenv("PMX_ABLATE");
     p.ablate = ab ? atoi(ab) : 0;
@@ -997,6 +1133,17 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   const int sms = ctx->sm_count - reserve_sms > 0 ? ctx->sm_count - reserve_sms : 1;
   int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;
+  {
+    // the setmaxnreg split must balance: registers released by warpgroup 0 >= registers requested by warpgroups 1-4
+    static int regs_ok = -1;
+    if (regs_ok < 0) {
+      cudaFuncAttributes fa;
+      PMX_CUDA(cudaFuncGetAttributes(&fa, k_grad_umma<1, false, false>));
+      regs_ok = (fa.numRegs >= PMX_REG_DEC && 128 * (fa.numRegs - PMX_REG_DEC) >= (NUM_THREADS - 128) * (PMX_REG_INC - fa.numRegs)) ? 1 : 0;
+      if (!regs_ok) pmx_set_error("k_grad_umma: compiled for %d registers, the setmaxnreg split %d/%d cannot be served", fa.numRegs, PMX_REG_DEC, PMX_REG_INC);
+    }
+    if (!regs_ok) return PMX_ERR_UNSUPPORTED;
+  }
   if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
   {
     // instantiations: k-halves (K <= 64 / K <= 128) x with / without the loss reduction x production / debug

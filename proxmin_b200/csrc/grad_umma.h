@@ -7,8 +7,19 @@ struct UmmaPlan;
 // shapes the tcgen05 kernel takes: K <= 128 (operands are zero-padded to K = 64 or, for K > 64, to 128 and handled
 // as two 64-deep k-halves), any M, any N
 bool umma_supported(int M, int N, int K);
-// Y: fp32 with a row pitch of ldY floats (any alignment: the kernel reads it with plain coalesced loads)
-int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out);
+// Y: fp32, two layouts:
+//   y_blocked = 0: row-major with a row pitch of ldY floats (any alignment: plain coalesced 4-byte loads);
+//   y_blocked = 1: tiled -- the layout of a solver handle's device copy of Y (pmx_nmf_set_Y builds it).  The matrix is
+//     cut into 128 x 128 tiles stored one after the other in the order the gradient kernel walks them (row block major);
+//     inside a tile: [32 row quads][128 columns][4 rows].  ldY = number of tiles per row block = ceil(N / 128); the
+//     buffer holds ceil(M / 128) * ldY tiles of 64 KB, padding zero, base 16-byte aligned.  A thread of the gradient
+//     kernel fetches 4 rows of its column with one 16-byte load, a warp instruction covers 512 contiguous bytes and a
+//     CTA streams one contiguous region (pmx_y_index below).
+int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K, UmmaPlan** out, int y_blocked = 0);
+__host__ __device__ inline size_t pmx_y_index(int m, int n, int ldY, int y_blocked) {
+  if (!y_blocked) return (size_t)m * ldY + n;
+  return ((((size_t)(m >> 7) * ldY + (n >> 7)) * 32 + ((m & 127) >> 2)) * 128 + (n & 127)) * 4 + (m & 3);
+}
 void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
 // skip_split != 0: the plan's bf16 (hi, lo) operand buffers already hold the split of (A, S) -- the fused update
 // kernels wrote them -- so the two split passes are skipped

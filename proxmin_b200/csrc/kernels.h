@@ -15,7 +15,11 @@ int launch_gram_reduce(pmx_ctx* ctx, cudaStream_t st, const float* part, int nbl
 int launch_lambda_max(pmx_ctx* ctx, cudaStream_t st, const double* gram, int C, pmx_ctl* ctl, int which);
 int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int which0, const double* gram1, int which1,
                        int C, pmx_ctl* ctl);
-int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, const float* A, const float* S, int M, int N, int K, float* GA,
+// rows [m0, m0 + nrows) x columns [col0, col0 + ncols) of Y from a row-major staging buffer (pitch floats per row) into the
+// tiled device copy (grad_umma.h); m0 is a multiple of 4
+int launch_y_interleave(pmx_ctx* ctx, cudaStream_t st, const float* stage, int pitch, int nrows, int ncols, float* Yb, int ldY,
+                        int m0, int col0);
+int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done);
 
 // solver_kernels.cu

@@ -15,6 +15,7 @@
 #include "pgm_tail.h"
 
 int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
+
 bool pmx_comm_has_aux(pmx_ctx* ctx);
 bool pmx_peer_available(pmx_ctx* ctx);
 int pmx_peer_arena(pmx_ctx* ctx, size_t bytes, pmx_peer_region** out);
@@ -27,7 +28,7 @@ struct pmx_nmf {
   pmx_ctx* ctx;
   int M, N, K;   // N = local number of columns (this rank's stripe of Y and S)
   double N_global; // total number of columns over all ranks (row means of S in step_adaprox)
-  int ldY;       // leading dimension of the device copy of Y (N rounded up to 4: TMA needs 16-byte row pitch)
+  int ldY;       // the device copy of Y is tiled (grad_umma.h): ldY = 128-column tiles per row block = ceil(N / 128)
   float *Y, *A, *S, *A_old, *S_old, *Ae, *Se, *GA, *GS;
   double *gramA, *gramS;
   pmx_ctl* ctl;     // device
@@ -60,6 +61,8 @@ struct pmx_nmf {
   size_t off_GA, off_A, off_Ahi, off_Alo, off_inbox;   // regions of the peer arena (bytes)
   cudaGraphExec_t tail_graph;
   long long tail_graph_launches;
+  bool tail_G_pending;         // the last gradients still sit in the parity buffers (tail_publish_G)
+  size_t tail_G_par;
   // ---- adaprox
   pmx_adaprox_opts ada;
   float *MA, *MS, *VA, *VS, *VhA, *VhS, *Psi, *Z0, *Z1, *alphaA, *alphaS;
@@ -125,13 +128,13 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
       pmx_set_error("tcgen05 gradient kernel does not support M=%d N=%d K=%d", h->M, h->N, h->K);
       return PMX_ERR_UNSUPPORTED;
     }
-    if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
+    if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan, 1));
     const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
     PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride, want));
     h->used_umma = true;
   } else {
     h->used_umma = false;
-    PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, A, S, h->M, h->N, h->K, GA, GS, loss, done));
+    PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, 1, A, S, h->M, h->N, h->K, GA, GS, loss, done));
   }
   if (ctx->world > 1) {
     if (!defer_reduce && (want & 1) && GA) PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
@@ -208,6 +211,8 @@ int nmf_global_cols(pmx_nmf* h) {
 
 extern "C" {
 
+static int tail_publish_G(pmx_nmf* h);
+
 int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   PMX_REQUIRE(ctx && out, "NULL argument");
   PMX_REQUIRE(M > 0 && N_local > 0 && K > 0, "shape must be positive");
@@ -218,11 +223,11 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   h->M = M;
   h->N = N_local;
   h->K = K;
-  h->ldY = (N_local + 3) & ~3;
+  h->ldY = pmx_div_up(N_local, 128);
   h->N_global = (double)N_local;
   PMX_CUDA(cudaSetDevice(ctx->device));
   const size_t mk = (size_t)M * K, kn = (size_t)K * N_local;
-  PMX_CHECK(alloc_f(h->ctx, &h->Y, (size_t)M * h->ldY));
+  PMX_CHECK(alloc_f(h->ctx, &h->Y, (size_t)pmx_div_up(M, 128) * h->ldY * 16384));   // tiled, see grad_umma.h
   PMX_CHECK(alloc_f(h->ctx, &h->A, mk));
   PMX_CHECK(alloc_f(h->ctx, &h->S, kn));
   PMX_CHECK(alloc_f(h->ctx, &h->A_old, mk));
@@ -235,7 +240,7 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   PMX_CUDA(cudaMemset(h->gramS, 0, sizeof(double) * (K * K + 4)));
   PMX_CUDA(cudaMalloc((void**)&h->ctl, sizeof(pmx_ctl)));
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), ctx->stream));
-  PMX_CUDA(cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)M * h->ldY, ctx->stream));
+  PMX_CUDA(cudaMemsetAsync(h->Y, 0, sizeof(float) * (size_t)pmx_div_up(M, 128) * h->ldY * 16384, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(h->GA, 0, sizeof(float) * mk, ctx->stream));
   PMX_CUDA(cudaMemsetAsync(h->GS, 0, sizeof(float) * kn, ctx->stream));
   PMX_CUDA(cudaMallocHost((void**)&h->h_ctl, sizeof(pmx_ctl)));
@@ -278,10 +283,51 @@ int pmx_nmf_destroy(pmx_nmf* h) {
 int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncols) {
   PMX_REQUIRE(h && host_Y, "NULL argument");
   PMX_REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= h->N, "column range outside the local stripe");
-  PMX_CUDA(cudaMemcpy2DAsync(h->Y + col0, sizeof(float) * h->ldY, host_Y, sizeof(float) * ld, sizeof(float) * ncols,
-                             h->M, cudaMemcpyHostToDevice, h->ctx->stream));
-  PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
-  return PMX_OK;
+  if (ncols == 0) return PMX_OK;
+  // The device copy is tiled (grad_umma.h).  Row chunks travel through two row-major staging buffers:
+  // the copy of chunk i + 1 (main stream) overlaps the interleave kernel of chunk i (side stream).
+  pmx_ctx* ctx = h->ctx;
+  const size_t pitch = ((size_t)ncols + 3) & ~(size_t)3;
+  size_t rows = ((size_t)48 << 20) / (pitch * sizeof(float));    // ~48 MB per staging buffer
+  rows = rows < 4 ? 4 : (rows & ~(size_t)3);
+  if (rows > (size_t)((h->M + 3) & ~3)) rows = (size_t)((h->M + 3) & ~3);
+  if (rows > 4 * 32768) rows = 4 * 32768;                          // grid.y of the interleave kernel
+  float* stage[2] = {nullptr, nullptr};
+  PMX_CHECK(alloc_f(ctx, &stage[0], rows * pitch));
+  PMX_CHECK(alloc_f(ctx, &stage[1], rows * pitch));
+  cudaEvent_t copied[2], used[2];
+  for (int i = 0; i < 2; ++i) {
+    PMX_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    PMX_CUDA(cudaEventCreateWithFlags(&used[i], cudaEventDisableTiming));
+  }
+  int st = PMX_OK, chunk = 0;
+  for (size_t m0 = 0; m0 < (size_t)h->M && st == PMX_OK; m0 += rows, ++chunk) {
+    const int b = chunk & 1;
+    const size_t nr = (size_t)h->M - m0 < rows ? (size_t)h->M - m0 : rows;
+    cudaError_t e = cudaSuccess;
+    if (chunk >= 2) e = cudaStreamWaitEvent(ctx->stream, used[b], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(stage[b], sizeof(float) * pitch, host_Y + m0 * ld, sizeof(float) * ld, sizeof(float) * ncols, nr,
+                            cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(copied[b], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux, copied[b], 0);
+    if (e != cudaSuccess) {
+      pmx_set_error("pmx_nmf_set_Y: %s", cudaGetErrorString(e));
+      st = PMX_ERR_CUDA;
+      break;
+    }
+    st = launch_y_interleave(ctx, ctx->aux, stage[b], (int)pitch, (int)nr, ncols, h->Y, h->ldY, (int)m0, col0);
+    if (st == PMX_OK && cudaEventRecord(used[b], ctx->aux) != cudaSuccess) st = PMX_ERR_CUDA;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->aux);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(copied[i]);
+    cudaEventDestroy(used[i]);
+  }
+  pmx_dev_free(ctx, stage[0]);
+  pmx_dev_free(ctx, stage[1]);
+  return st;
 }
 
 static int which_ptr(pmx_nmf* h, int which, float** p, size_t* n) {
@@ -323,12 +369,14 @@ int pmx_nmf_get(pmx_nmf* h, int which, float* host_dst) {
   PMX_REQUIRE(h && host_dst, "NULL argument");
   float* p; size_t n;
   PMX_CHECK(which_ptr(h, which, &p, &n));
+  if (which == PMX_GA || which == PMX_GS) PMX_CHECK(tail_publish_G(h));
   return pmx_d2h(h->ctx, host_dst, p, n * sizeof(float));
 }
 
 int pmx_nmf_device_ptr(pmx_nmf* h, int which, float** dev_ptr) {
   PMX_REQUIRE(h && dev_ptr, "NULL argument");
   size_t n;
+  if (which == PMX_GA || which == PMX_GS) PMX_CHECK(tail_publish_G(h));
   return which_ptr(h, which, dev_ptr, &n);
 }
 
@@ -393,6 +441,7 @@ static int tail_setup(pmx_nmf* h) {
   pmx_ctx* ctx = h->ctx;
   h->tail_mode = false;
   h->tail_ready = false;
+  h->tail_G_pending = false;
   if (h->tail_graph) {
     cudaGraphExecDestroy(h->tail_graph);
     h->tail_graph = nullptr;
@@ -442,7 +491,7 @@ static float* tail_ga_base(pmx_nmf* h) {
 static int tail_prologue(pmx_nmf* h) {
   pmx_ctx* ctx = h->ctx;
   const int* done = &h->ctl->done;
-  if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan));
+  if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan, 1));
   if (ctx->world > 1) {
     char* loc = static_cast<char*>(ctx->peer_arena.local);
     PMX_CHECK(umma_plan_use_A(h->plan, loc + h->off_Ahi, loc + h->off_Alo));
@@ -482,10 +531,14 @@ static int tail_args(pmx_nmf* h, PgmTailArgs* out) {
   a.Shi = (unsigned short*)Shi; a.Slo = (unsigned short*)Slo; a.ldS = ldS;
   a.chS = h->chS;
   a.nS = pgm_tail_s_blocks(ctx, h->N, &a.n_tiles_S);
-  // rows of A this rank updates (reduce-scatter slice): an even split of the M rows, PMX_TAIL_RA rows per block
+  // rows of A this rank updates (reduce-scatter slice): an even split of the M rows, a.ra rows per block
   a.m_lo = (int)((long long)h->M * ctx->rank / ctx->world);
   a.m_hi = (int)((long long)h->M * (ctx->rank + 1) / ctx->world);
-  a.nA = pmx_div_up(a.m_hi - a.m_lo, PMX_TAIL_RA);
+  // (a sharded run has few rows per rank and every A block starts with remote loads: smaller blocks keep at least
+  // ~64 of them in flight so that the exchange is one NVLink round trip deep instead of several)
+  a.ra = PMX_TAIL_RA;
+  while (a.ra > 8 && pmx_div_up(a.m_hi - a.m_lo, a.ra) < 64) a.ra >>= 1;
+  a.nA = pmx_div_up(a.m_hi - a.m_lo, a.ra);
   a.chA = h->chA;
   a.ldA = ldA;
   a.ga_stride = (long long)h->ga_stride;
@@ -541,21 +594,32 @@ static int tail_close(pmx_nmf* h) {
   return launch_tail_final(h->ctx, h->ctx->stream, a);
 }
 
-// after a run: the last gradients (algorithms.py:144 hands them back) and, sharded, the replicated A leave the
-// parity / arena buffers for the plain ones that pmx_nmf_get and the other solvers read
+// after a run: sharded, the replicated A leaves the arena for the plain buffer that pmx_nmf_get and the other solvers
+// read.  The last gradients (algorithms.py:144 hands them back) stay in their parity buffers until somebody asks for
+// them (tail_publish_G, from pmx_nmf_get / pmx_nmf_device_ptr): two 16 MB copies and, sharded, an all-reduce of the
+// G_A partials that a loop which only polls the stop flag never needs.
 static int tail_publish(pmx_nmf* h) {
   pmx_ctx* ctx = h->ctx;
-  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
-  const size_t par = (size_t)(h->h_ctl->it & 1);
-  if (h->h_ctl->it > 0) {
-    PMX_CUDA(cudaMemcpyAsync(h->GS, h->GS2 + par * h->gs_stride, sizeof(float) * kn, cudaMemcpyDeviceToDevice, ctx->stream));
-    PMX_CUDA(cudaMemcpyAsync(h->GA, tail_ga_base(h) + par * h->ga_stride, sizeof(float) * mk, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->GA, mk, 0, ctx->stream));
-  }
+  const size_t mk = (size_t)h->M * h->K;
+  h->tail_G_pending = h->h_ctl->it > 0;
+  h->tail_G_par = (size_t)(h->h_ctl->it & 1);
   if (ctx->world > 1 && h->tail_ready)
     PMX_CUDA(cudaMemcpyAsync(h->A, static_cast<char*>(ctx->peer_arena.local) + h->off_A, sizeof(float) * mk,
                              cudaMemcpyDeviceToDevice, ctx->stream));
   PMX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMX_OK;
+}
+
+static int tail_publish_G(pmx_nmf* h) {
+  if (!h->tail_G_pending) return PMX_OK;
+  pmx_ctx* ctx = h->ctx;
+  const size_t mk = (size_t)h->M * h->K, kn = (size_t)h->K * h->N;
+  const size_t par = h->tail_G_par;
+  PMX_CUDA(cudaMemcpyAsync(h->GS, h->GS2 + par * h->gs_stride, sizeof(float) * kn, cudaMemcpyDeviceToDevice, ctx->stream));
+  PMX_CUDA(cudaMemcpyAsync(h->GA, tail_ga_base(h) + par * h->ga_stride, sizeof(float) * mk, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->GA, mk, 0, ctx->stream));
+  PMX_CUDA(cudaStreamSynchronize(ctx->stream));
+  h->tail_G_pending = false;
   return PMX_OK;
 }
 
@@ -1066,7 +1130,7 @@ int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, i
     umma_plan_destroy(ctx, plan);
     return st;
   }
-  return launch_grad_simt(ctx, Y, N, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);
+  return launch_grad_simt(ctx, Y, N, 0, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);
 }
 
 int pmx_nmf_lipschitz(pmx_ctx* ctx, const float* A, const float* S, int M, int N, int K, float* lip_A_host,

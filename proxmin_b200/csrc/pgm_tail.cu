@@ -36,7 +36,7 @@ namespace {
 
 constexpr int TT = 256;
 constexpr int CT_COLS = 32, CT_RPT = 8, CT_LD = 68;   // S tile: 32 columns x 64 rows, stored column-major (ld 68)
-constexpr int RA = PMX_TAIL_RA;                       // rows of A per A block
+constexpr int RA = PMX_TAIL_RA;                       // rows of A per A block (upper bound; a.ra is the actual count)
 constexpr int NREP = PMX_TAIL_NREP;                   // replicated accumulators of the Gram partials
 constexpr long long SPIN_LIMIT = 6000000000LL;        // ~3 s of SM clocks: a lost peer must not hang the GPU
 
@@ -278,8 +278,8 @@ __device__ __forceinline__ void s_role(const PgmTailArgs& a, unsigned par, float
 __device__ __forceinline__ void a_role(const PgmTailArgs& a, unsigned par, float step, unsigned char* smem, int* s_fault) {
   const int K = a.K, world = a.world;
   const int ablk = blockIdx.x;
-  const int m0 = a.m_lo + ablk * RA;
-  const int nrows = min(RA, a.m_hi - m0);
+  const int m0 = a.m_lo + ablk * a.ra;
+  const int nrows = min(a.ra, a.m_hi - m0);
   float* at = reinterpret_cast<float*>(smem);                               // [RA][K + 1] new values (Gram operand)
   float(*red)[8] = reinterpret_cast<float(*)[8]>(at + RA * (K + 1));
   const int ldt = K + 1;

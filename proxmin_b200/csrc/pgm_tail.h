@@ -2,7 +2,7 @@
 #pragma once
 #include "prox.cuh"
 
-#define PMX_TAIL_RA 64     // rows of A per A block
+#define PMX_TAIL_RA 64     // rows of A per A block (upper bound)
 #define PMX_TAIL_NREP 8    // replicated fp32 accumulators of the per-block Gram partials
 
 struct PgmTailArgs {
@@ -19,6 +19,7 @@ struct PgmTailArgs {
   int n_tiles_S, nS;        // 32-column tiles and the number of S blocks (= first block index of the A blocks)
   // ---- A block (replicated; this rank updates rows [m_lo, m_hi))
   int m_lo, m_hi, nA;
+  int ra;                   // rows of A per A block (<= PMX_TAIL_RA)
   ProxChain chA;
   int ldA;                  // row pitch (elements) of the bf16 A operand buffers
   long long ga_stride;      // elements between the two G_A buffers
