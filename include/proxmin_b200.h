@@ -96,7 +96,10 @@ typedef enum {
   PMX_OP_MIN = 4,   /* operators.py:55-69   X[X-t<0] = t                  */
   PMX_OP_MAX = 5,   /* operators.py:72-84   X[X-t>0] = t                  */
   PMX_OP_HARD = 6,  /* operators.py:109-125 X[|X|<t] = 0                  */
-  PMX_OP_SOFT = 7   /* operators.py:138-150 sign(X)*max(|X|-t,0)          */
+  PMX_OP_SOFT = 7,  /* operators.py:138-150 sign(X)*max(|X|-t,0)          */
+  PMX_OP_MAXENT = 8,   /* operators.py:163-184 X[X>0] = t W(exp(X/t - 1)/t), W = Lambert W, t = gamma (*step);
+                          fp32 semantics of the reference: exp overflows to inf for X/t > 89 */
+  PMX_OP_MAXENT64 = 9  /* same for a caller array of dtype float64: the reference then evaluates exp in fp64 */
 } pmx_op_code;
 
 typedef struct {
@@ -138,6 +141,12 @@ int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out);
 int pmx_nmf_destroy(pmx_nmf* h);
 /* upload rows x cols host block (leading dimension ld, in elements) of Y starting at column col0 */
 int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncols);
+/* weights of the weighted likelihood (nmf.py:25, 40: D = W (A S - Y), sum W (Y - A S)^2 / 2): an M x N host matrix
+ * uploaded like Y; once set, every gradient / loss of this handle is weighted */
+int pmx_nmf_set_W(pmx_nmf* h, const float* host_W, size_t ld, int col0, int ncols);
+/* nmf.py:28-41 at the handle's current (A, S): gradients into the GA / GS buffers (pmx_nmf_get), optionally the
+ * log-likelihood (nmf.py:13-25) */
+int pmx_nmf_gradient(pmx_nmf* h, double* loss_host_or_null);
 int pmx_nmf_set(pmx_nmf* h, int which, const float* host_src);
 int pmx_nmf_get(pmx_nmf* h, int which, float* host_dst);
 int pmx_nmf_device_ptr(pmx_nmf* h, int which, float** dev_ptr);
@@ -231,10 +240,17 @@ typedef enum {
                          red = |X|^2 |Z'|^2 |U'(/s1)|^2 |R|^2 |S|^2   utils.py:299-303,349-363 */
   PMX_EW_DOT_DIFF = 5,/* red = sum((a-b)*c), sum((a-b)^2)         algorithms.py:118                */
   PMX_EW_MAXABS = 6,  /* red[0] = max|s0*a|                       algorithms.py:121                */
-  PMX_EW_SUMSQ = 7    /* red[0] = sum(a^2)                        utils.py:257-260                 */
+  PMX_EW_SUMSQ = 7,   /* red[0] = sum(a^2)                        utils.py:257-260                 */
+  PMX_EW_AXPY = 9,    /* o0 = s0*a + b   (b may be NULL)              utils.py:316,333 with a dense L  */
+  PMX_EW_BB = 8       /* a=X b=X_prev c=G d=G_prev: red = sum(S^2) sum(S*Y) sum(Y^2) sum(G^2), S = a-b, Y = c-d
+                         (Barzilai-Borwein step sizes)                utils.py:225-239                 */
 } pmx_ew_op;
 int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const float* c, const float* d, float s0,
            float s1, float* o0, float* o1, float* o2, double* red_host);
+
+/* dense linear operator of admm / sdmm / bsdmm (utils.py:38-101 MatrixAdapter.dot, :316, :333, :299-303):
+ * O[p x m] = op(L)[p x n] X[n x m], all device, row-major, fp32; trans != 0: op(L) = L^T with L stored n x p. */
+int pmx_matmul(pmx_ctx* ctx, const float* L, const float* X, float* O, int p, int n, int m, int trans);
 
 /* sums along an axis of a device matrix: out_host has cols (axis 0) or rows (axis 1) doubles (nmf.py:91-93 means) */
 int pmx_axis_sum(pmx_ctx* ctx, const float* X, int rows, int cols, int axis, double* out_host);

@@ -98,6 +98,15 @@ def prox_soft_plus(X, step, thresh=0, type="relative"):  # operators.py:153-160
     return X
 
 
+def prox_max_entropy(X, step, gamma=1, type="relative"):  # operators.py:163-184
+    from scipy.special import lambertw
+
+    gamma_ = _thr(step, gamma, type)
+    above = X > 0
+    X[above] = gamma_ * np.real(lambertw(np.exp(X[above] / gamma_ - 1) / gamma_))
+    return X
+
+
 class AlternatingProjections:  # operators.py:187-224
     def __init__(self, prox_list=None, repeat=1):
         self.operators = list(prox_list) if prox_list is not None else []
@@ -144,34 +153,98 @@ class Nesterov:  # utils.py:193-206; the t-sequence advances on every read of .o
         return om
 
 
+class Adapter:  # utils.py:38-101 (MatrixAdapter) for L = None or a dense matrix, axis=None
+    def __init__(self, L):
+        spec = None
+        while isinstance(L, Adapter):  # prevent cascade (:44-48)
+            spec = L._spec
+            L = L.L
+        self.L, self._spec = L, spec
+
+    @property
+    def spectral_norm(self):  # :53-60
+        if self._spec is None:
+            self._spec = lipschitz(self.L)
+        return self._spec
+
+    @property
+    def T(self):  # :62-67
+        if self.L is None:
+            return self
+        return Adapter(self.L.T)
+
+    def dot(self, X):  # :69-77: with L = None the argument itself is returned (not a copy)
+        if self.L is None:
+            return X
+        return self.L.dot(X)
+
+
+class BarzilaiBorweinStepper:  # utils.py:209-241
+    def __init__(self, type=1, init_r=0.1):
+        assert type in [1, 2]
+        self.r = init_r
+        self.type = type
+
+    def step(self, *X, it=None, grads=None):
+        N = len(X)
+        if it == 0:
+            self.Delta = np.array([np.inf, ] * N)
+            self.X_ = tuple(x.copy() for x in X)
+            self.G_ = grads
+            return tuple(self.r * np.max(np.abs(X[j])) / np.max(np.abs(grads[j])) for j in range(N))
+        G = grads
+        S = tuple(X[j] - self.X_[j] for j in range(N))
+        Y = tuple(G[j] - self.G_[j] for j in range(N))
+        self.X_ = tuple(x.copy() for x in X)
+        self.G_ = grads
+        if self.type == 1:
+            A = tuple(np.sum(S[j] ** 2) / np.sum(S[j] * Y[j]) for j in range(N))
+        else:
+            A = tuple(np.sum(S[j] * Y[j]) / np.sum(Y[j] ** 2) for j in range(N))
+        if it <= 3:
+            self.Delta = np.minimum(self.Delta, tuple(np.sqrt(np.sum(S[j] ** 2)) for j in range(N)))
+        Astab = tuple(self.Delta[j] / np.sqrt(np.sum(G[j] ** 2)) for j in range(N))
+        return np.minimum(np.abs(A), Astab)
+
+
 def _tup(X):  # utils.py:8-12
     return X if type(X) in (list, tuple) else (X,)
 
 
-def _init_zu(X, m=None):
-    # utils.py:244-254 with MatrixAdapter(None): L.dot(X) is X itself, so Z = X.copy(), U = 0
-    if m is None:
-        return X.copy(), np.zeros(X.shape, dtype=X.dtype)
-    return [X.copy() for _ in range(m)], [np.zeros(X.shape, dtype=X.dtype) for _ in range(m)]
+_ID = Adapter(None)
 
 
-def _mm(X, Z, U, prox_g, step_g):
-    # utils.py:295-304 with L = identity (LX is X, L.T.dot(v) is v)
-    Znew = prox_g(X + U, step_g)
-    R = X - Znew
-    S = -1 / step_g * (Znew - Z)
+def _init_zu(X, L=_ID):
+    # utils.py:244-254; with MatrixAdapter(None) L.dot(X) is X itself, so Z = X.copy(), U = 0
+    if not isinstance(L, list):
+        Z = L.dot(X).copy()
+        U = np.zeros(Z.shape, dtype=Z.dtype)
+    else:
+        Z, U = [], []
+        for i in range(len(L)):
+            Z.append(L[i].dot(X).copy())
+            U.append(np.zeros(Z[i].shape, dtype=Z[i].dtype))
+    return Z, U
+
+
+def _mm(X, Z, U, prox_g, step_g, L=_ID):
+    # utils.py:295-304
+    LX = L.dot(X)
+    Znew = prox_g(LX + U, step_g)
+    R = LX - Znew
+    S = -1 / step_g * L.T.dot(Znew - Z)
     Z[:] = Znew[:]
     U[:] += R
-    return X, R, S
+    return LX, R, S
 
 
-def _update_variables(X, Z, U, prox_f, step_f, prox_g, step_g):
-    # utils.py:307-346 with L = identity
+def _update_variables(X, Z, U, prox_f, step_f, prox_g, step_g, L=_ID):
+    # utils.py:307-346
     if not hasattr(prox_g, "__iter__"):
         if prox_g is not None:  # utils.py:315-318
-            dX = step_f / step_g * (X - Z + U)
+            dX = step_f / step_g * L.T.dot(L.dot(X) - Z + U)
             X[:] = prox_f(X - dX, step_f)
-            return _mm(X, Z, U, prox_g, step_g)
+            return _mm(X, Z, U, prox_g, step_g, L)
         S = -X.copy()  # utils.py:319-327 (no constraint: fixed-point iteration on f)
         X[:] = prox_f(X, step_f)
         Z[:] = X[:]
@@ -179,28 +252,28 @@ def _update_variables(X, Z, U, prox_f, step_f, prox_g, step_g):
         S += X
         return X, R, S
     m = len(prox_g)  # utils.py:329-345
-    dX = np.sum([step_f / step_g[i] * (X - Z[i] + U[i]) for i in range(m)], axis=0)
+    dX = np.sum([step_f / step_g[i] * L[i].T.dot(L[i].dot(X) - Z[i] + U[i]) for i in range(m)], axis=0)
     X[:] = prox_f(X - dX, step_f)
     LX, R, S = [None] * m, [None] * m, [None] * m
     for i in range(m):
-        LX[i], R[i], S[i] = _mm(X, Z[i], U[i], prox_g[i], step_g[i])
+        LX[i], R[i], S[i] = _mm(X, Z[i], U[i], prox_g[i], step_g[i], L[i])
     return LX, R, S
 
 
-def _constraint_converged(X, LX, Z, U, R, S, step_g, e_rel, e_abs, is_list):
-    # utils.py:366-391 (+ get_variable_errors :349-363) with ||L|| = 1
-    if is_list:
+def _constraint_converged(X, LX, Z, U, R, S, step_g, e_rel, e_abs, L=_ID):
+    # utils.py:366-391 (+ get_variable_errors :349-363)
+    if isinstance(L, list):
         ok, errs = True, []
-        for i in range(len(Z)):
-            c, e = _constraint_converged(X, LX[i], Z[i], U[i], R[i], S[i], step_g[i], e_rel, e_abs, False)
+        for i in range(len(L)):
+            c, e = _constraint_converged(X, LX[i], Z[i], U[i], R[i], S[i], step_g[i], e_rel, e_abs, L[i])
             ok &= c
             errs.append(e)
         return ok, errs
-    e_pri = np.sqrt(Z.size) * e_abs / 1 + e_rel * np.max([l2(LX), l2(Z)])
+    e_pri = np.sqrt(Z.size) * e_abs / L.spectral_norm + e_rel * np.max([l2(LX), l2(Z)])
     if step_g is not None:
-        e_dual = np.sqrt(X.size) * e_abs / 1 + e_rel * l2(U / step_g)
+        e_dual = np.sqrt(X.size) * e_abs / L.spectral_norm + e_rel * l2(L.T.dot(U) / step_g)
     else:
-        e_dual = np.sqrt(X.size) * e_abs / 1 + e_rel * l2(U)
+        e_dual = np.sqrt(X.size) * e_abs / L.spectral_norm + e_rel * l2(L.T.dot(U))
     lR, lS = l2(R), l2(S)
     return (lR <= e_pri) and (lS <= e_dual), (e_pri, e_dual, lR, lS)
 
@@ -374,19 +447,20 @@ def adaprox(X, grad, step, prox=None, scheme="adam", b1=0.9, b2=0.999, eps=1e-8,
     return converged, M, V, Vhat, it + 1, sub
 
 
-def admm(X, prox_f, step_f, prox_g=None, step_g=None, e_rel=1e-6, e_abs=0, max_iter=1000, callback=None):
-    """algorithms.py:426-520 with L=None.  Returns (converged, errors, logged_iterations)."""
-    Z, U = _init_zu(X)
+def admm(X, prox_f, step_f, prox_g=None, step_g=None, L=None, e_rel=1e-6, e_abs=0, max_iter=1000, callback=None):
+    """algorithms.py:426-520 (L = None or dense).  Returns (converged, errors, logged_iterations)."""
+    _L = Adapter(L)
+    Z, U = _init_zu(X, _L)
     it, slack = 0, 1.0
     converged, error = False, None
     while it < max_iter:
         if callback is not None:
             callback(X, it=it)  # un-starred (:480)
         sf = slack * step_f(X, it=it)
-        sg = sf * 1 * 1 * 1 if (prox_g is not None and step_g is None) else step_g  # :485-488, utils.py:279
-        LX, R, S = _update_variables(X, Z, U, prox_f, sf, prox_g, sg)
+        sg = sf * _L.spectral_norm * 1 * 1 if (prox_g is not None and step_g is None) else step_g  # :485-488, utils.py:279
+        LX, R, S = _update_variables(X, Z, U, prox_f, sf, prox_g, sg, _L)
         # quirk (:494-496): tolerances use the *user* step_g (None by default), not sg
-        converged, error = _constraint_converged(X, LX, Z, U, R, S, step_g, e_rel, e_abs, False)
+        converged, error = _constraint_converged(X, LX, Z, U, R, S, step_g, e_rel, e_abs, _L)
         if converged:
             break
         it += 1
@@ -394,44 +468,48 @@ def admm(X, prox_f, step_f, prox_g=None, step_g=None, e_rel=1e-6, e_abs=0, max_i
             if it > 1 and (X == Xprev).all() and (R == Rprev).all():  # noqa: F821
                 slack /= 2
                 it = 0
-                Z, U = _init_zu(X)
+                Z, U = _init_zu(X, _L)
             Xprev = X.copy()
             Rprev = R
     return converged, error, it + 1
 
 
-def sdmm(X, prox_f, step_f, proxs_g=None, steps_g=None, e_rel=1e-6, e_abs=0, max_iter=1000, callback=None):
-    """algorithms.py:523-650 with Ls=None.  Returns (converged, logged_iterations)."""
+def sdmm(X, prox_f, step_f, proxs_g=None, steps_g=None, Ls=None, e_rel=1e-6, e_abs=0, max_iter=1000, callback=None):
+    """algorithms.py:523-650 (Ls = None or dense).  Returns (converged, logged_iterations)."""
     if proxs_g is None or not hasattr(proxs_g, "__iter__"):  # :568-579 (drops e_abs)
-        c, _, n = admm(X, prox_f, step_f, prox_g=proxs_g, step_g=steps_g, e_rel=e_rel,
+        c, _, n = admm(X, prox_f, step_f, prox_g=proxs_g, step_g=steps_g, L=Ls, e_rel=e_rel,
                        max_iter=max_iter, callback=callback)
         return c, n
     m = len(proxs_g)
-    Z, U = _init_zu(X, m)
+    if not hasattr(Ls, "__iter__"):  # :585-587
+        Ls = [Ls] * m
+    assert len(Ls) == m
+    _L = [Adapter(Ls[i]) for i in range(m)]
+    Z, U = _init_zu(X, _L)
     it, slack = 0, 1.0
     converged = False
     while it < max_iter:
         if callback is not None:
             callback(X, it=it)
         sf = slack * step_f(X, it=it)
-        sg = [sf * 1 * 1 * m for _ in range(m)] if steps_g is None else steps_g  # :611-616
-        LX, R, S = _update_variables(X, Z, U, prox_f, sf, proxs_g, sg)
-        converged, _ = _constraint_converged(X, LX, Z, U, R, S, sg, e_rel, e_abs, True)  # :624-626
+        sg = [sf * _L[i].spectral_norm * 1 * m for i in range(m)] if steps_g is None else steps_g  # :611-616
+        LX, R, S = _update_variables(X, Z, U, prox_f, sf, proxs_g, sg, _L)
+        converged, _ = _constraint_converged(X, LX, Z, U, R, S, sg, e_rel, e_abs, _L)  # :624-626
         if converged:
             break
         it += 1
         if it > 1 and (X == Xprev).all() and all((R[i] == Rprev[i]).all() for i in range(m)):  # noqa: F821
             slack /= 2
             it = 0
-            Z, U = _init_zu(X, m)
+            Z, U = _init_zu(X, _L)
         Rprev = R
         Xprev = X.copy()
     return converged, it + 1
 
 
-def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, update_order=None, max_iter=1000,
+def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, Ls=None, update_order=None, max_iter=1000,
           e_rel=1e-6, e_abs=0, callback=None):
-    """algorithms.py:653-850 for Ls=None, steps_g=None, steps_g_update='steps_f'.
+    """algorithms.py:653-850 for steps_g=None, steps_g_update='steps_f' (Ls = None or dense).
 
     Returns (converged list, iterations)."""
     N = len(X)
@@ -444,6 +522,10 @@ def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, update_order=None, max_iter=1000
         e_abs = [e_abs] * N
     if update_order is None:
         update_order = range(N)
+    if not hasattr(Ls, "__iter__"):  # :754-755
+        Ls = [Ls] * N
+    Ls = list(Ls)
+    assert len(Ls) == N
     Mj = [0] * N
     proxs_g = list(proxs_g)
     for j in range(N):
@@ -451,9 +533,18 @@ def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, update_order=None, max_iter=1000
             if not hasattr(proxs_g[j], "__iter__"):
                 proxs_g[j] = [proxs_g[j]]
             Mj[j] = len(proxs_g[j])
+            if not hasattr(Ls[j], "__iter__"):  # :766-767
+                Ls[j] = [Ls[j]] * Mj[j]
+            assert len(Ls[j]) == Mj[j]
+    _L = []
+    for j in range(N):  # :773-781
+        if proxs_g[j] is None:
+            _L.append(Adapter(None))
+        else:
+            _L.append([Adapter(Ls[j][m]) for m in range(Mj[j])])
     Z, U = [], []
     for j in range(N):  # :787-790
-        z, u = _init_zu(X[j], None if proxs_g[j] is None else Mj[j])
+        z, u = _init_zu(X[j], _L[j])
         Z.append(z)
         U.append(u)
     converged = [None] * N
@@ -467,10 +558,9 @@ def bsdmm(X, proxs_f, steps_f_cb, proxs_g=None, update_order=None, max_iter=1000
             if proxs_g[j] is None:
                 sg = None
             else:
-                sg = [sf * 1 * N * Mj[j] for _ in range(Mj[j])]  # :815-819, utils.py:279
-            LX, R, S = _update_variables(X[j], Z[j], U[j], pf, sf, proxs_g[j], sg)
-            converged[j], _ = _constraint_converged(X[j], LX, Z[j], U[j], R, S, sg, e_rel[j], e_abs[j],
-                                                    proxs_g[j] is not None)
+                sg = [sf * _L[j][i].spectral_norm * N * Mj[j] for i in range(Mj[j])]  # :815-819, utils.py:279
+            LX, R, S = _update_variables(X[j], Z[j], U[j], pf, sf, proxs_g[j], sg, _L[j])
+            converged[j], _ = _constraint_converged(X[j], LX, Z[j], U[j], R, S, sg, e_rel[j], e_abs[j], _L[j])
         it += 1
         if all(converged):
             break

@@ -88,6 +88,74 @@ def maxabs(x, scale=1.0):
     return ew(_ffi.EW_MAXABS, x, s0=scale, n_out=0, reduce=True)[1][0]
 
 
+def bb_sums(X, Xold, G, Gold):
+    """(sum(S*S), sum(S*Y), sum(Y*Y), sum(G*G)) with S = X - Xold, Y = G - Gold   (utils.py:225-239)"""
+    r = ew(_ffi.EW_BB, X, Xold, G, Gold, n_out=0, reduce=True)[1]
+    return r[0], r[1], r[2], r[3]
+
+
+class DeviceMatrix(object):
+    """A dense linear operator kept resident on the device: ``dot(X)`` = L X and ``Tdot(X)`` = L^T X upload only the
+    argument (utils.py:76-77; the operators of admm / sdmm / bsdmm, utils.py:299-303, :316, :333)."""
+
+    def __init__(self, L):
+        self.L32 = _f32(L)
+        assert self.L32.ndim == 2, "linear operator must be a matrix"
+        self.shape = self.L32.shape
+        self.dtype = np.asarray(L).dtype
+        self.ctx = _ffi.context()
+        self.ptr = self.ctx.upload(self.L32)
+
+    def close(self):
+        if self.ptr is not None:
+            self.ctx.free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass
+
+    def _mul(self, X, trans):
+        X32 = _f32(X)
+        vec = X32.ndim == 1
+        Xm = np.ascontiguousarray(X32.reshape(-1, 1) if vec else X32)
+        rows, cols = self.shape
+        p, n = (cols, rows) if trans else (rows, cols)
+        if Xm.shape[0] != n:
+            raise ValueError("shapes %s and %s not aligned" % ((p, n), X32.shape))
+        m = Xm.shape[1]
+        with _Scope() as sc:
+            pX = sc.up(Xm)
+            pO = sc.alloc(4 * max(p * m, 1))
+            _ffi.check(_ffi.lib().pmx_matmul(sc.ctx.handle, self.ptr, pX, pO, p, n, m, 1 if trans else 0))
+            out = sc.down(pO, (p, m))
+        dt = np.result_type(self.dtype, np.asarray(X).dtype)
+        out = out.astype(dt if dt.kind == "f" else np.float64, copy=False)
+        return out.reshape(p) if vec else out
+
+    def dot(self, X):
+        return self._mul(X, False)
+
+    def Tdot(self, X):
+        return self._mul(X, True)
+
+
+def matmul(L, X):
+    """L.dot(X) for a dense matrix L (p x n) and a vector (n,) or matrix (n x m) X on the device."""
+    dm = DeviceMatrix(L)
+    try:
+        return dm.dot(X)
+    finally:
+        dm.close()
+
+
+def axpy(s, a, b=None):
+    """s * a + b (b optional), two roundings like NumPy."""
+    return ew(_ffi.EW_AXPY, a, b, s0=s)[0][0].astype(np.asarray(a).dtype, copy=False)
+
+
 def admm_xarg(X, Zs, Us, ratios):
     """X - sum_i ratio_i (X - Z_i + U_i)   (utils.py:316-317, 331-338)"""
     dX = None

@@ -12,11 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libproxmin_b200.so")
 
 PMX_MAX_OPS = 8
-OP_ID, OP_ZERO, OP_PLUS, OP_UNITY, OP_MIN, OP_MAX, OP_HARD, OP_SOFT = range(8)
+OP_ID, OP_ZERO, OP_PLUS, OP_UNITY, OP_MIN, OP_MAX, OP_HARD, OP_SOFT, OP_MAXENT, OP_MAXENT64 = range(10)
 A, S, GA, GS, MA, MS, VA, VS, VHA, VHS = range(10)
 SCHEMES = {"adam": 0, "nadam": 1, "amsgrad": 2, "padam": 3, "adamx": 4, "radam": 5}
 
-EW_EXTRAP, EW_ADD, EW_SUB, EW_DX_ACC, EW_ZU, EW_DOT_DIFF, EW_MAXABS, EW_SUMSQ = range(8)
+EW_EXTRAP, EW_ADD, EW_SUB, EW_DX_ACC, EW_ZU, EW_DOT_DIFF, EW_MAXABS, EW_SUMSQ, EW_BB, EW_AXPY = range(10)
 ERR_CUDA, ERR_ARG, ERR_NCCL, ERR_UNSUPPORTED, ERR_NONFINITE = -1, -2, -3, -4, -5
 
 
@@ -107,6 +107,8 @@ def _declare(L):
         "pmx_nmf_create": [vp, i32, i32, i32, C.POINTER(vp)],
         "pmx_nmf_destroy": [vp],
         "pmx_nmf_set_Y": [vp, vp, sz, i32, i32],
+        "pmx_nmf_set_W": [vp, vp, sz, i32, i32],
+        "pmx_nmf_gradient": [vp, pd],
         "pmx_nmf_set": [vp, i32, vp],
         "pmx_nmf_get": [vp, i32, vp],
         "pmx_nmf_device_ptr": [vp, i32, C.POINTER(vp)],
@@ -126,6 +128,7 @@ def _declare(L):
         "pmx_admm_run": [vp, C.c_double, i32, pi, pi, pd],
         "pmx_pgm_update": [vp, C.POINTER(Prox), vp, vp, vp, i32, i32, f32, pd, pd],
         "pmx_axis_sum": [vp, vp, i32, i32, i32, pd],
+        "pmx_matmul": [vp, vp, vp, vp, i32, i32, i32, i32],
         "pmx_ew": [vp, i32, sz, vp, vp, vp, vp, f32, f32, vp, vp, vp, pd],
         "pmx_adaprox_moments": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, f32, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_double, i32, pf],

@@ -31,16 +31,46 @@ logger = logging.getLogger("proxmin")
 # ------------------------------------------------------------------------------------------
 # recognition of library callables
 # ------------------------------------------------------------------------------------------
-def _nmf_grad_target(grad):
-    """Y if ``grad`` is partial(nmf.grad_likelihood, Y=Y[, W=1]); else None."""
+def _nmf_grad_target(grad, weighted=False):
+    """Y if ``grad`` is partial(nmf.grad_likelihood, Y=Y[, W=1]); else None.  ``weighted=True``: also accept an M x N
+    weight matrix and return ``(Y, W)`` (W is None for W == 1)."""
     from . import nmf as _nmf
 
     if isinstance(grad, partial) and grad.func is _nmf.grad_likelihood and not grad.args:
         kw = grad.keywords or {}
         W = kw.get("W", 1)
-        if "Y" in kw and set(kw) <= {"Y", "W"} and np.ndim(W) == 0 and W == 1 and np.ndim(kw["Y"]) == 2:
-            return kw["Y"]
-    return None
+        if "Y" in kw and set(kw) <= {"Y", "W"} and np.ndim(kw["Y"]) == 2:
+            if np.ndim(W) == 0 and W == 1:
+                return (kw["Y"], None) if weighted else kw["Y"]
+            if weighted and np.ndim(W) == 2 and np.shape(W) == np.shape(kw["Y"]):
+                return kw["Y"], W
+    return (None, None) if weighted else None
+
+
+class _ResidentGradient(object):
+    """grad(*X) of the NMF likelihood for the callback loops: Y (and W) stay on the device in a solver handle, every
+    call uploads the two factors, runs the fused gradient kernel and downloads the two gradients (nmf.py:28-41)."""
+
+    def __init__(self, Y, W):
+        self.Y, self.W, self.prob = Y, W, None
+
+    def __call__(self, *X):
+        from . import nmf as _nmf
+
+        A, S = X
+        if self.prob is None:
+            self.prob = _nmf.Problem(self.Y, A, S, W=self.W)
+        else:
+            self.prob.set(_ffi.A, A)
+            self.prob.set(_ffi.S, S)
+        self.prob.gradient()
+        dt = np.result_type(A.dtype, S.dtype)
+        return self.prob.get(_ffi.GA, dtype=dt), self.prob.get(_ffi.GS, dtype=dt)
+
+    def close(self):
+        if self.prob is not None:
+            self.prob.close()
+            self.prob = None
 
 
 def _is_step(step, fn_name):
@@ -121,6 +151,8 @@ def _dev_pgm_update(ops, Xe, G, X, step, Xold=None):
 
 def _scalar_step(s):
     if np.ndim(s) != 0:
+        if np.size(s) == 1:      # e.g. BarzilaiBorweinStepper: np.minimum(...) of one variable, shape (1,)
+            return float(np.asarray(s).reshape(-1)[0])
         raise NotImplementedError("array-valued step sizes are not supported by the callback loop")
     return float(s)
 
@@ -161,6 +193,14 @@ def pgm(
     if (Y is not None and chains is not None and _is_factor_pair(X) and _is_step(step, "step_pgm")
             and not backtracking):
         return _pgm_nmf_device(X, Y, chains, accelerated, e_rel, max_iter, callback)
+    Yw, Ww = _nmf_grad_target(grad, weighted=True)
+    if Yw is not None and _is_factor_pair(X):
+        # user step / prox / backtracking with the library's gradient: Y (and W) stay resident on the device
+        resident = _ResidentGradient(Yw, Ww)
+        try:
+            return _pgm_callbacks(X, resident, step, prox, accelerated, backtracking, f, e_rel, max_iter, callback)
+        finally:
+            resident.close()
     return _pgm_callbacks(X, grad, step, prox, accelerated, backtracking, f, e_rel, max_iter, callback)
 
 
@@ -340,11 +380,19 @@ def adaprox(
     if Vhat is not None:
         assert len(Vhat) == N and all(vhat.shape == x.shape for x, vhat in zip(X, Vhat))
 
-    Y = _nmf_grad_target(grad)
+    Y, W = _nmf_grad_target(grad, weighted=True)
     chains = _describe_all(prox, allow_none=True)
     if (Y is not None and chains is not None and _is_factor_pair(X) and _is_step(step, "step_adaprox")):
+        # (step_adaprox does not depend on W, nmf.py:91-93: the weighted likelihood takes the fused loop as well)
         return _adaprox_nmf_device(X, Y, chains, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter,
-                                   prox_max_iter, M, V, Vhat, callback)
+                                   prox_max_iter, M, V, Vhat, callback, W=W)
+    if Y is not None and _is_factor_pair(X):
+        resident = _ResidentGradient(Y, W)
+        try:
+            return _adaprox_callbacks(X, resident, step, prox, scheme, b1, b2, eps, check_convergence, p, e_rel,
+                                      max_iter, prox_max_iter, M, V, Vhat, callback)
+        finally:
+            resident.close()
     return _adaprox_callbacks(X, grad, step, prox, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter,
                               prox_max_iter, M, V, Vhat, callback)
 
@@ -355,12 +403,12 @@ def _b1_prev(b1):
 
 
 def _adaprox_nmf_device(X, Y, chains, scheme, b1, b2, eps, check_convergence, p, e_rel, max_iter, prox_max_iter,
-                        M, V, Vhat, callback):
+                        M, V, Vhat, callback, W=None):
     from . import nmf as _nmf
 
     A, S = X
     dt = np.result_type(A.dtype, S.dtype)
-    prob = _nmf.Problem(Y, A, S)
+    prob = _nmf.Problem(Y, A, S, W=W)
     b1 = np.asarray(b1, dtype=np.float64)
     b1p = _b1_prev(b1)
     try:
@@ -473,68 +521,105 @@ def _adaprox_callbacks(X, grad, step, prox, scheme, b1, b2, eps, check_convergen
 
 
 # ------------------------------------------------------------------------------------------
-# ADMM family (L = identity)
+# ADMM family
 # ------------------------------------------------------------------------------------------
-def _no_L(L):
+def _linop(L):
+    """None for the identity (fast paths below), else a utils.MatrixAdapter holding a dense matrix resident on the
+    device (utils.py:38-101).  Sparse operators raise NotImplementedError."""
     if L is None:
-        return
-    if hasattr(L, "__iter__") and not hasattr(L, "shape"):
-        for l in L:
-            _no_L(l)
-        return
-    raise NotImplementedError("linear operators L / Ls other than None (identity) are outside the B200 hot path "
-                              "(SURVEY.md section 8-f row 3)")
+        return None
+    ad = L if isinstance(L, utils.MatrixAdapter) else utils.MatrixAdapter(L)
+    return None if ad.L is None else ad
 
 
-def _step_g_of(step_f, N=1, M=1):
-    return step_f * 1 * N * M  # utils.py:279 with ||L||^2 = 1
+def _spec(L):
+    return 1 if L is None else L.spectral_norm
 
 
-def _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g=True):
-    """utils.py:295-304 for L = identity.  Returns (LX, R, S, norms)."""
+def _step_g_of(step_f, N=1, M=1, norm_L2=1):
+    return step_f * norm_L2 * N * M  # utils.py:279
+
+
+def _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g=True, L=None):
+    """utils.py:295-304.  Returns (LX, R, S, norms) with norms = (|LX|, |Z'|, |L^T U'(/step_g)|, |R|, |S|).
+    L = None is the identity (one fused kernel for R, S, U and the five norms); a dense L adds device GEMMs for
+    L X, L^T (Z' - Z) and L^T U."""
+    LX = X if L is None else L.dot(X)
     if chain_g is not None:
-        Znew = _dev.add(X, U)
+        Znew = _dev.add(LX, U)
         operators._apply(Znew, step_g, chain_g)
     else:
-        Znew = prox_g(_dev.add(X, U), step_g)
-    R, S, norms = _dev.admm_zu(X, Znew, Z, U, step_g, dual_uses_step_g)
-    return X, R, S, norms
+        Znew = prox_g(_dev.add(LX, U), step_g)
+    R, S, norms = _dev.admm_zu(LX, Znew, Z, U, step_g, dual_uses_step_g)
+    if L is None:
+        return X, R, S, norms
+    S = L.T.dot(S)                                       # S = -1/step_g L^T (Z' - Z)   (utils.py:300)
+    lS = np.sqrt(np.float32(_dev.sumsq(S)))
+    lU = np.sqrt(np.float32(_dev.sumsq(L.T.dot(U))))     # l2(L^T U [/ step_g])          (utils.py:359-362)
+    if dual_uses_step_g:
+        lU = lU / np.float32(step_g)
+    return LX, R, S, (norms[0], norms[1], lU, norms[3], lS)
 
 
-def _update_variables(X, Z, U, prox_f, step_f, prox_g, chain_g, step_g, dual_uses_step_g=True):
-    """utils.py:307-346 for L = identity.  Returns (LX, R, S, norms) -- lists in the multi-constraint case."""
+def _dX_arg(X, Zs, Us, ratios, Ls):
+    """X - sum_i ratio_i L_i^T (L_i X - Z_i + U_i)   (utils.py:316-317, 331-338)"""
+    if all(l is None for l in Ls):
+        return _dev.admm_xarg(X, Zs, Us, ratios)
+    dX = None
+    for Z, U, r, L in zip(Zs, Us, ratios, Ls):
+        LX = X if L is None else L.dot(X)
+        t = _dev.ew(_ffi.EW_DX_ACC, LX, Z, U, None, s0=1.0)[0][0]        # L X - Z + U
+        if L is not None:
+            t = L.T.dot(t)
+        dX = _dev.axpy(r, t, dX)
+    return _dev.ew(_ffi.EW_SUB, X, dX)[0][0].astype(X.dtype, copy=False)
+
+
+def _update_variables(X, Z, U, prox_f, step_f, prox_g, chain_g, step_g, dual_uses_step_g=True, L=None):
+    """utils.py:307-346.  Returns (LX, R, S, norms) -- lists in the multi-constraint case.  L: None (identity), a
+    MatrixAdapter, or a list of those."""
     if not hasattr(prox_g, "__iter__"):
         if prox_g is not None:
-            X[:] = prox_f(_dev.admm_xarg(X, [Z], [U], [step_f / step_g]), step_f)
-            return _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g)
+            X[:] = prox_f(_dX_arg(X, [Z], [U], [step_f / step_g], [L]), step_f)
+            return _mm(X, Z, U, prox_g, chain_g, step_g, dual_uses_step_g, L=L)
         Xold = X.copy()
         X[:] = prox_f(X, step_f)
         Z[:] = X[:]
         R = np.zeros(X.shape, dtype=X.dtype)
         S = _dev.ew(_ffi.EW_SUB, X, Xold)[0][0].astype(X.dtype, copy=False)
         nX = np.sqrt(np.float32(_dev.sumsq(X)))
-        norms = (nX, nX, np.sqrt(np.float32(_dev.sumsq(U))), np.float32(0), np.sqrt(np.float32(_dev.sumsq(S))))
+        LTU = U if L is None else L.T.dot(U)
+        norms = (nX, nX, np.sqrt(np.float32(_dev.sumsq(LTU))), np.float32(0), np.sqrt(np.float32(_dev.sumsq(S))))
         return X, R, S, norms
     m = len(prox_g)
-    X[:] = prox_f(_dev.admm_xarg(X, Z, U, [step_f / step_g[i] for i in range(m)]), step_f)
+    Ls = L if isinstance(L, list) else [L] * m
+    X[:] = prox_f(_dX_arg(X, Z, U, [step_f / step_g[i] for i in range(m)], Ls), step_f)
     LX, R, S, norms = [None] * m, [None] * m, [None] * m, [None] * m
     for i in range(m):
-        LX[i], R[i], S[i], norms[i] = _mm(X, Z[i], U[i], prox_g[i], chain_g[i], step_g[i], dual_uses_step_g)
+        LX[i], R[i], S[i], norms[i] = _mm(X, Z[i], U[i], prox_g[i], chain_g[i], step_g[i], dual_uses_step_g, L=Ls[i])
     return LX, R, S, norms
 
 
-def _constraint_convergence(size, norms, e_rel, e_abs):
-    """utils.py:349-391 for ||L|| = 1 from the five device norms of one constraint."""
+def _constraint_convergence(size, norms, e_rel, e_abs, p=None, spec=1):
+    """utils.py:349-391 from the five device norms of one constraint; size = X.size, p = Z.size, spec = ||L||_s^2
+    (the reference divides by L.spectral_norm, the squared norm: utils.py:357-362)."""
     lLX, lZ, lU, lR, lS = norms
-    e_pri = np.sqrt(size) * e_abs / 1 + e_rel * np.max([lLX, lZ])
-    e_dual = np.sqrt(size) * e_abs / 1 + e_rel * lU
+    p = size if p is None else p
+    e_pri = np.sqrt(p) * e_abs / spec + e_rel * np.max([lLX, lZ])
+    e_dual = np.sqrt(size) * e_abs / spec + e_rel * lU
     return (lR <= e_pri) and (lS <= e_dual), (e_pri, e_dual, lR, lS)
 
 
-def _init_zu(X, m=None):
+def _init_zu(X, m=None, L=None):
+    """utils.py:244-254: Z = L X (a copy), U = 0 per constraint."""
+    def one(l):
+        Z = X.copy() if l is None else np.array(l.dot(X), copy=True)
+        return Z, np.zeros(Z.shape, dtype=Z.dtype)
     if m is None:
-        return X.copy(), np.zeros(X.shape, dtype=X.dtype)
-    return [X.copy() for _ in range(m)], [np.zeros(X.shape, dtype=X.dtype) for _ in range(m)]
+        return one(L)
+    Ls = L if isinstance(L, list) else [L] * m
+    pairs = [one(l) for l in Ls]
+    return [z for z, _ in pairs], [u for _, u in pairs]
 
 
 def _admm_device(X, b, step_value, chains, e_rel, e_abs, max_iter, dual_uses_step_g):
@@ -583,11 +668,12 @@ def admm(
     max_iter=1000,
     callback=None,
 ):
-    """Linearised ADMM with one constraint (algorithms.py:426-520).  Returns ``(converged, errors)``."""
-    _no_L(L)
+    """Linearised ADMM with one constraint (algorithms.py:426-520).  Returns ``(converged, errors)``.
+    ``L``: None (identity), a dense matrix or a ``utils.MatrixAdapter`` (device GEMMs); sparse raises."""
+    _L = _linop(L)
     chain_g = _device_chain(prox_g) if prox_g is not None else None
 
-    if (prox_g is not None and step_g is None and callback is None
+    if (_L is None and prox_g is not None and step_g is None and callback is None
             and _fusable_admm(X, prox_f, step_f, [chain_g])):
         # quirk kept: the tolerances of `admm` use the user's step_g (None) -> no division of U (algorithms.py:494-496)
         converged, errors, logged = _admm_device(X, prox_f.b, step_f.value, [chain_g], e_rel, e_abs, max_iter,
@@ -597,7 +683,7 @@ def admm(
             logger.warning("Solution did not converge")
         return converged, errors[0]
 
-    Z, U = _init_zu(X)
+    Z, U = _init_zu(X, L=_L)
     it = 0
     slack = 1.0
     if callback is None:
@@ -607,12 +693,12 @@ def admm(
         callback(X, it=it)
         step_f_ = slack * step_f(X, it=it)
         if prox_g is not None and step_g is None:
-            step_g_ = _step_g_of(step_f_)
+            step_g_ = _step_g_of(step_f_, norm_L2=_spec(_L))
         else:
             step_g_ = step_g
         LX, R, S, norms = _update_variables(X, Z, U, prox_f, step_f_, prox_g, chain_g, step_g_,
-                                            dual_uses_step_g=step_g is not None)
-        converged, error = _constraint_convergence(X.size, norms, e_rel, e_abs)
+                                            dual_uses_step_g=step_g is not None, L=_L)
+        converged, error = _constraint_convergence(X.size, norms, e_rel, e_abs, p=Z.size, spec=_spec(_L))
         if converged:
             break
         it += 1
@@ -621,7 +707,7 @@ def admm(
                 if (X == X_).all() and (R == R_).all():  # noqa: F821
                     slack /= 2
                     it = 0
-                    Z, U = _init_zu(X)
+                    Z, U = _init_zu(X, L=_L)
                     logger.info("Restarting with step size slack = %.3f" % slack)
             X_ = X.copy()
             R_ = R
@@ -649,11 +735,15 @@ def sdmm(
         # fall back to admm, dropping e_abs like the reference (algorithms.py:568-579)
         return admm(X, prox_f, step_f, prox_g=proxs_g, step_g=steps_g, L=Ls, e_rel=e_rel, max_iter=max_iter,
                     callback=callback)
-    _no_L(Ls)
     M = len(proxs_g)
+    if not hasattr(Ls, "__iter__") or hasattr(Ls, "shape"):   # None or single: M duplicates (algorithms.py:585-587)
+        Ls = [Ls] * M
+    assert len(Ls) == M
+    _L = [_linop(l) for l in Ls]
+    identity = all(l is None for l in _L)
     chains = [_device_chain(pg) for pg in proxs_g]
 
-    if steps_g is None and callback is None and _fusable_admm(X, prox_f, step_f, chains):
+    if identity and steps_g is None and callback is None and _fusable_admm(X, prox_f, step_f, chains):
         converged, _, logged = _admm_device(X, prox_f.b, step_f.value, chains, e_rel, e_abs, max_iter,
                                             dual_uses_step_g=True)
         logger.info("Completed {0} iterations".format(logged))
@@ -661,7 +751,7 @@ def sdmm(
             logger.warning("Solution did not converge")
         return converged
 
-    Z, U = _init_zu(X, M)
+    Z, U = _init_zu(X, M, L=_L)
     it = 0
     slack = 1.0
     if callback is None:
@@ -671,13 +761,13 @@ def sdmm(
         callback(X, it=it)
         step_f_ = slack * step_f(X, it=it)
         if steps_g is None:
-            steps_g_ = [_step_g_of(step_f_, M=M) for i in range(M)]
+            steps_g_ = [_step_g_of(step_f_, M=M, norm_L2=_spec(_L[i])) for i in range(M)]
         else:
             steps_g_ = steps_g
-        LX, R, S, norms = _update_variables(X, Z, U, prox_f, step_f_, proxs_g, chains, steps_g_)
+        LX, R, S, norms = _update_variables(X, Z, U, prox_f, step_f_, proxs_g, chains, steps_g_, L=_L)
         converged = True
         for i in range(M):
-            c, _ = _constraint_convergence(X.size, norms[i], e_rel, e_abs)
+            c, _ = _constraint_convergence(X.size, norms[i], e_rel, e_abs, p=Z[i].size, spec=_spec(_L[i]))
             converged &= c
         if converged:
             break
@@ -686,7 +776,7 @@ def sdmm(
             if (X == X_).all() and all([(R[i] == R_[i]).all() for i in range(M)]):  # noqa: F821
                 slack /= 2
                 it = 0
-                Z, U = _init_zu(X, M)
+                Z, U = _init_zu(X, M, L=_L)
                 logger.info("Restarting with step size slack = %.3f" % slack)
         R_ = R
         X_ = X.copy()
@@ -721,7 +811,6 @@ def bsdmm(
     assert len(proxs_g) == N
     steps_g_update = steps_g_update.lower()
     assert steps_g_update in ["steps_f", "fixed", "relative"]
-    _no_L(Ls)
     if steps_g is not None and steps_g_update != "steps_f":
         raise NotImplementedError("steps_g_update='fixed'/'relative' with explicit steps_g (experts-only option)")
 
@@ -733,18 +822,28 @@ def bsdmm(
         update_order = range(N)
 
     proxs_g = list(proxs_g)
+    # Ls None or single: N duplicates; per block: M_j duplicates (algorithms.py:754-770)
+    if not hasattr(Ls, "__iter__") or hasattr(Ls, "shape"):
+        Ls = [Ls] * N
+    Ls = list(Ls)
+    assert len(Ls) == N
     M = [0] * N
     chains = [None] * N
+    _L = [None] * N
     for j in range(N):
         if proxs_g[j] is not None:
             if not hasattr(proxs_g[j], "__iter__"):
                 proxs_g[j] = [proxs_g[j]]
             M[j] = len(proxs_g[j])
             chains[j] = [_device_chain(pg) for pg in proxs_g[j]]
+            if not hasattr(Ls[j], "__iter__") or hasattr(Ls[j], "shape"):
+                Ls[j] = [Ls[j]] * M[j]
+            assert len(Ls[j]) == M[j]
+            _L[j] = [_linop(l) for l in Ls[j]]
 
     Z, U = [], []
     for j in range(N):
-        z, u = _init_zu(X[j], None if proxs_g[j] is None else M[j])
+        z, u = _init_zu(X[j], None if proxs_g[j] is None else M[j], L=_L[j])
         Z.append(z)
         U.append(u)
 
@@ -761,15 +860,16 @@ def bsdmm(
             if proxs_g[j] is None:
                 steps_g_j = None
             else:
-                steps_g_j = [_step_g_of(steps_f_j, N=N, M=M[j]) for i in range(M[j])]
+                steps_g_j = [_step_g_of(steps_f_j, N=N, M=M[j], norm_L2=_spec(_L[j][i])) for i in range(M[j])]
             LX, R, S, norms = _update_variables(X[j], Z[j], U[j], proxs_f_j, steps_f_j, proxs_g[j], chains[j],
-                                                steps_g_j)
+                                                steps_g_j, L=_L[j])
             if proxs_g[j] is None:
                 converged[j], _ = _constraint_convergence(X[j].size, norms, e_rel[j], e_abs[j])
             else:
                 ok = True
                 for i in range(M[j]):
-                    c, _ = _constraint_convergence(X[j].size, norms[i], e_rel[j], e_abs[j])
+                    c, _ = _constraint_convergence(X[j].size, norms[i], e_rel[j], e_abs[j], p=Z[j][i].size,
+                                                   spec=_spec(_L[j][i]))
                     ok &= c
                 converged[j] = ok
         it += 1
@@ -787,7 +887,10 @@ def _bsdmm_nmf(Y, A, S, W, prox_A, prox_S, max_iter, e_rel, callback, proxs_g=No
     fused on the device (gradient kernel + Lipschitz steps + ADMM variable updates per block)."""
     from . import nmf as _nmf
 
-    _nmf._check_W(W)
+    if _nmf._check_W(W) is not None:
+        # the reference's default step closure evaluates `if W == 1` on the weight matrix (nmf.py:63, 188-193)
+        raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                         "Use a.any() or a.all()")
     unsupported = set(kw) - {"steps_g", "Ls", "update_order", "steps_g_update"}
     if unsupported:
         raise TypeError("bsdmm() got unexpected keyword arguments %s" % sorted(unsupported))

@@ -279,7 +279,7 @@ static int check_prox(const pmx_prox* p) {
   PMX_REQUIRE(p != nullptr, "prox is NULL");
   PMX_REQUIRE(p->n_ops >= 0 && p->n_ops <= PMX_MAX_OPS, "prox chain length out of range");
   for (int i = 0; i < p->n_ops; ++i) {
-    PMX_REQUIRE(p->ops[i].op >= PMX_OP_ID && p->ops[i].op <= PMX_OP_SOFT, "unknown prox op code");
+    PMX_REQUIRE(p->ops[i].op >= PMX_OP_ID && p->ops[i].op <= PMX_OP_MAXENT64, "unknown prox op code");
     if (p->ops[i].op == PMX_OP_UNITY) PMX_REQUIRE(p->ops[i].axis == 0 || p->ops[i].axis == 1, "UNITY axis must be 0 or 1");
   }
   return PMX_OK;

@@ -82,6 +82,17 @@ __global__ void __launch_bounds__(kT) k_ew(EwArgs e) {
       case PMX_EW_SUMSQ:       // l2sq(a)                                   utils.py:257-260
         r[0] = fmaf(e.a[i], e.a[i], r[0]);
         break;
+      case PMX_EW_AXPY:        // s0 * a + b (two roundings, like NumPy)       utils.py:316, 333
+        e.o0[i] = e.b ? __fadd_rn(__fmul_rn(e.s0, e.a[i]), e.b[i]) : __fmul_rn(e.s0, e.a[i]);
+        break;
+      case PMX_EW_BB: {        // S = X - X_, Y = G - G_                    utils.py:225-239
+        const float sd = e.a[i] - e.b[i], yd = e.c[i] - e.d[i], g = e.c[i];
+        r[0] = fmaf(sd, sd, r[0]);
+        r[1] = fmaf(sd, yd, r[1]);
+        r[2] = fmaf(yd, yd, r[2]);
+        r[3] = fmaf(g, g, r[3]);
+        break;
+      }
     }
   }
   if (!e.red) return;
@@ -118,7 +129,7 @@ extern "C" {
 int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const float* c, const float* d, float s0,
            float s1, float* o0, float* o1, float* o2, double* red_host) {
   PMX_REQUIRE(ctx != nullptr, "ctx is NULL");
-  PMX_REQUIRE(op >= PMX_EW_EXTRAP && op <= PMX_EW_SUMSQ, "unknown elementwise opcode");
+  PMX_REQUIRE(op >= PMX_EW_EXTRAP && op <= PMX_EW_AXPY, "unknown elementwise opcode");
   double* d_red = nullptr;
   if (red_host) {
     PMX_CUDA(cudaMalloc((void**)&d_red, 5 * sizeof(double)));
@@ -154,6 +165,59 @@ int pmx_ew(pmx_ctx* ctx, int op, size_t n, const float* a, const float* b, const
     }
   }
   return st;
+}
+
+// ---------------------------------------------------------------- dense linear operators  (utils.py:76-77)
+// O[p x m] = L[p x n] X[n x m], fp32 with fma accumulation: the L.dot(X) / L.T.dot(..) of admm / sdmm / bsdmm with a
+// non-identity L (utils.py:316, 333, 299-303).  L is small on this path (a K x K coupling or a p x n design matrix of a
+// few thousand columns): a 32 x 32 shared-memory tiled kernel is all it needs.
+}  // extern "C"
+namespace {
+constexpr int MT = 32;
+__global__ void __launch_bounds__(MT * 8) k_matmul(const float* __restrict__ L, const float* __restrict__ X,
+                                                   float* __restrict__ O, int p, int n, int m, int trans) {
+  __shared__ float sL[MT][MT + 1];
+  __shared__ float sX[MT][MT + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, 4 output rows per thread
+  const int col = blockIdx.x * MT + tx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < n; k0 += MT) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int lr = ty + 8 * r;
+      const int gi = blockIdx.y * MT + lr, gk = k0 + tx;
+      sL[lr][tx] = (gi < p && gk < n) ? (trans ? L[(size_t)gk * p + gi] : L[(size_t)gi * n + gk]) : 0.f;
+      const int xk = k0 + lr;
+      sX[lr][tx] = (xk < n && col < m) ? X[(size_t)xk * m + col] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < MT; ++k) {
+      const float xv = sX[k][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sL[ty + 8 * r][k], xv, acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int gi = blockIdx.y * MT + ty + 8 * r;
+    if (gi < p && col < m) O[(size_t)gi * m + col] = acc[r];
+  }
+}
+}  // namespace
+extern "C" {
+
+int pmx_matmul(pmx_ctx* ctx, const float* L, const float* X, float* O, int p, int n, int m, int trans) {
+  PMX_REQUIRE(ctx && L && X && O, "NULL argument");
+  PMX_REQUIRE(p > 0 && n > 0 && m > 0, "shape must be positive");
+  dim3 grid((unsigned)pmx_div_up(m, MT), (unsigned)pmx_div_up(p, MT));
+  PMX_REQUIRE(grid.y <= 65535, "too many rows for pmx_matmul");
+  k_matmul<<<grid, MT * 8, 0, ctx->stream>>>(L, X, O, p, n, m, trans);
+  PMX_LAUNCHED(ctx);
+  PMX_CHECK(pmx_check_launch(ctx, "k_matmul"));
+  PMX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PMX_OK;
 }
 
 // sums along an axis of a device matrix (np.mean / np.sum building block, nmf.py:91-93); out_host: cols (axis 0) or rows (axis 1) doubles

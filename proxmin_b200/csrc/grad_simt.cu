@@ -13,7 +13,7 @@ namespace {
 constexpr int BM = 64, BN = 64;
 constexpr int LDR = BN + 1;  // residual tile row stride (odd: conflict-free row-strided reads)
 
-__global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, int ldY, int y_blocked, const float* __restrict__ A,
+__global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, const float* __restrict__ W, int ldY, int y_blocked, const float* __restrict__ A,
                                                    const float* __restrict__ S, int M, int N, int K,
                                                    float* __restrict__ GA, float* __restrict__ GS,
                                                    double* __restrict__ loss, const int* done) {
@@ -69,9 +69,14 @@ __global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, 
       for (int q = 0; q < 4; ++q) {
         const int m = m_base + m0 + p, n = n_base + n0 + q;
         float d = 0.f;
-        if (m < M && n < N) d = r[p][q] - Y[pmx_y_index(m, n, ldY, y_blocked)];  // nmf.py:40 (W == 1)
+        float rr = 0.f;
+        if (m < M && n < N) {
+          const size_t yi = pmx_y_index(m, n, ldY, y_blocked);
+          rr = r[p][q] - Y[yi];                                                  // nmf.py:40
+          d = W ? W[yi] * rr : rr;                                               // D = W (A S - Y)
+        }
         sR[(m0 + p) * LDR + n0 + q] = d;
-        loss_part = fmaf(d, d, loss_part);
+        loss_part = fmaf(d, rr, loss_part);                                      // nmf.py:25: sum W (Y - A S)^2 / 2
       }
     __syncthreads();
     // G_A[m, k] += sum_n R[m, n] S[k, n]         (nmf.py:41, D.dot(S.T))
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ Y, 
 }  // namespace
 
 // G_A, G_S (and *loss) must be zeroed by the caller-facing wrapper: done here on the same stream.
-int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
+int launch_grad_simt(pmx_ctx* ctx, const float* Y, const float* W, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done) {
   if (K > 128) {
     pmx_set_error("SIMT gradient kernel supports K <= 128 (got %d)", K);
@@ -133,7 +138,7 @@ int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, int y_blocked, const
   const long long ntiles = (long long)pmx_div_up(M, BM) * pmx_div_up(N, BN);
   long long blocks = ntiles < (long long)ctx->sm_count * 4 ? ntiles : (long long)ctx->sm_count * 4;
   if (blocks < 1) return PMX_OK;
-  k_grad_simt<<<(int)blocks, 256, smem, ctx->stream>>>(Y, ldY, y_blocked, A, S, M, N, K, GA, GS, loss, done);
+  k_grad_simt<<<(int)blocks, 256, smem, ctx->stream>>>(Y, W, ldY, y_blocked, A, S, M, N, K, GA, GS, loss, done);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_grad_simt");
 }

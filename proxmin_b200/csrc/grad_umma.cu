@@ -296,6 +296,7 @@ struct Params {
   int NS;                 // 128-column stripes per m-block row
   long long total_tiles;  // m-blocks * NS
   const float* Y;         // fp32, row pitch ldY floats
+  const float* W;         // weights (WGT instantiations only): same layout as Y, tiled
   int ldY;
   float* GA;
   const unsigned* ga_epoch;   // parity counter: the gradients go to buffer (*ga_epoch + 1) & 1 of a pair (sharded runs: the
@@ -347,7 +348,8 @@ __device__ __forceinline__ uint32_t ring_use_G(int t, int kh, int ntiles) {
 
 // KH: number of 64-deep k-halves (1: K <= 64, 2: K <= 128)
 // LOSS: accumulate |R|^2 / 2 (nmf.py:25); DBG: timing ablations and the clock64 trace (never used for results)
-template <int KH, bool LOSS, bool DBG>
+// WGT: weighted likelihood, D = W (A S - Y) (nmf.py:25, 40) with a second M x N stream W in the same tiled layout
+template <int KH, bool LOSS, bool DBG, bool WGT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
             const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmShi,
@@ -710,7 +712,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     // (profiles/README.md, round-2 ablations).  The buffer index must be a compile-time constant (registers), hence
     // the tile loop below is unrolled three times.
     float y[48];
-    auto issue_y_half = [&](auto BUF, const TilePos& q, int h) {
+    auto issue_y_half = [&](auto BUF, const TilePos& q, int h, const float* Ybase) {
       constexpr int B0 = 16 * decltype(BUF)::value;
       if (ABL(8)) {
 #pragma unroll
@@ -723,7 +725,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         // bytes, a CTA streams its tile range as one contiguous region (the tile sequence is the storage order) and
         // there are no edge cases: the padding of the device copy is zero
         // (timing ablation 64: every tile reads tile (0, 0): same instructions, L2 hits instead of DRAM)
-        const float* src4 = p.Y + ((size_t)(ABL(64) ? 0 : q.mb * NS + q.st) * (TILE_M * TILE_N) +
+        const float* src4 = Ybase + ((size_t)(ABL(64) ? 0 : q.mb * NS + q.st) * (TILE_M * TILE_N) +
                                    (size_t)(grp * 8 + h * 4) * (TILE_N * 4) + row * 4);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -734,7 +736,7 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       }
       // row-major Y (pmx_nmf_grad on a caller's matrix): for a fixed row the 32 lanes read one 128-byte line
       const int m0 = q.mb * TILE_M + grp * 32 + h * 16, n0 = q.st * TILE_N;
-      const float* src = p.Y + (size_t)m0 * ldY + (n0 + row);
+      const float* src = Ybase + (size_t)m0 * ldY + (n0 + row);
       const uint32_t pitch = (uint32_t)ldY * 4u;
       const uint64_t a0 = reinterpret_cast<uint64_t>(src);
       uint32_t lo = (uint32_t)a0;
@@ -853,18 +855,23 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
     using IC0 = std::integral_constant<int, 0>;
     using IC1 = std::integral_constant<int, 1>;
     using IC2 = std::integral_constant<int, 2>;
+    // WGT: no rotation -- buffers 0 and 1 hold the two Y halves of the coming tile, buffer 2 the first half of W; the
+    // second half of W is fetched inside the conversion (its latency is exposed: the weighted pass streams twice the
+    // bytes and is not the tuned path)
     if (ntiles > 0) {
-      issue_y_half(IC0{}, pos0, 0);
-      issue_y_half(IC1{}, pos0, 1);
-      if (ntiles > 1) {
+      issue_y_half(IC0{}, pos0, 0, p.Y);
+      issue_y_half(IC1{}, pos0, 1, p.Y);
+      if constexpr (WGT) {
+        issue_y_half(IC2{}, pos0, 0, p.W);
+      } else if (ntiles > 1) {
         TilePos q1 = pos0;
         q1.next(NS);
-        issue_y_half(IC2{}, q1, 0);
+        issue_y_half(IC2{}, q1, 0, p.Y);
       }
     }
     // one tile; ROT = t % 3 selects the register buffers: first half in buffer YA, second half in buffer YB
     auto tile_body = [&](auto ROT, const int t) {
-      constexpr int YA = (2 * decltype(ROT)::value) % 3, YB = (2 * decltype(ROT)::value + 1) % 3;
+      constexpr int YA = WGT ? 0 : (2 * decltype(ROT)::value) % 3, YB = WGT ? 1 : (2 * decltype(ROT)::value + 1) % 3;
       const uint32_t slot = t & 1;
       mbar_wait(bar(B_ACC_FULL + slot), (t >> 1) & 1);
       tc_fence_after();
@@ -882,11 +889,22 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
         uint32_t acc[16];
         tmem_ld16(lane_addr + TM_ACC + slot * 128 + grp * 32 + h * 16, acc);
         tmem_ld_wait();
+        if constexpr (WGT) {
+          if (h == 1) issue_y_half(IC2{}, pos, 1, p.W);   // buffer 2 (first half of W) was consumed by h = 0
+        }
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float r0 = __uint_as_float(acc[j]) - y[(h == 0 ? YA : YB) * 16 + j];          // nmf.py:40  (A S - Y)
-          const float r1 = __uint_as_float(acc[j + 1]) - y[(h == 0 ? YA : YB) * 16 + j + 1];
-          if (LOSS) {
+          float r0 = __uint_as_float(acc[j]) - y[(h == 0 ? YA : YB) * 16 + j];          // nmf.py:40  (A S - Y)
+          float r1 = __uint_as_float(acc[j + 1]) - y[(h == 0 ? YA : YB) * 16 + j + 1];
+          if constexpr (WGT) {                                                            // D = W (A S - Y)
+            const float d0 = y[32 + j] * r0, d1 = y[32 + j + 1] * r1;
+            if (LOSS) {                                                                   // sum W (Y - A S)^2 / 2
+              loss_part = fmaf(d0, r0, loss_part);
+              loss_part = fmaf(d1, r1, loss_part);
+            }
+            r0 = d0;
+            r1 = d1;
+          } else if (LOSS) {
             loss_part = fmaf(r0, r0, loss_part);
             loss_part = fmaf(r1, r1, loss_part);
           }
@@ -932,8 +950,16 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
       // Issued after the hand-offs above so that load-queue back pressure never delays the MMA issuers
       // (re-loading every Y register right after its use was measured 8 % slower in round 1: the load issue then
       // sits on the path to the R^T hand-off)
-      if (t + 1 < ntiles) issue_y_half(std::integral_constant<int, YA>{}, nxt, 1);
-      if (t + 2 < ntiles) issue_y_half(std::integral_constant<int, YB>{}, nxt2, 0);
+      if constexpr (WGT) {
+        if (t + 1 < ntiles) {
+          issue_y_half(IC0{}, nxt, 0, p.Y);
+          issue_y_half(IC1{}, nxt, 1, p.Y);
+          issue_y_half(IC2{}, nxt, 0, p.W);
+        }
+      } else {
+        if (t + 1 < ntiles) issue_y_half(std::integral_constant<int, YA>{}, nxt, 1, p.Y);
+        if (t + 2 < ntiles) issue_y_half(std::integral_constant<int, YB>{}, nxt2, 0, p.Y);
+      }
       // ---- gradient flushes, one tile behind so that they never wait for the tensor pipe in steady state
       if (t > 0) {
         if constexpr (!GS1) flush_gs(prev, t - 1);
@@ -1020,6 +1046,7 @@ struct UmmaPlan {
   void *Ahi_own, *Alo_own;      // the plan's own A buffers (Ahi/Alo may point at external ones, umma_plan_use_A)
   CUtensorMap tmAhi, tmAlo, tmShi, tmSlo;
   int y_blocked;
+  const float* W;               // weights in the tiled layout of Y, or nullptr (umma_plan_set_W)
 };
 
 bool umma_supported(int M, int N, int K) { return K >= 1 && K <= 2 * KP && M >= 1 && N >= 1; }
@@ -1068,6 +1095,10 @@ int umma_plan_create(pmx_ctx* ctx, const float* Y, int ldY, int M, int N, int K,
     PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    PMX_CUDA(cudaFuncSetAttribute(k_grad_umma<2, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     attr = true;
   }
   *out = pl;
@@ -1079,6 +1110,15 @@ int umma_plan_use_A(UmmaPlan* pl, void* Ahi, void* Alo) {
   pl->Alo = Alo ? Alo : pl->Alo_own;
   PMX_CHECK(make_map(&pl->tmAhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Ahi, pl->KPT, (uint64_t)pl->Mp, pl->KPT * 2, KP, TILE_M));
   PMX_CHECK(make_map(&pl->tmAlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl->Alo, pl->KPT, (uint64_t)pl->Mp, pl->KPT * 2, KP, TILE_M));
+  return PMX_OK;
+}
+
+int umma_plan_set_W(UmmaPlan* pl, const float* W) {
+  if (W && !pl->y_blocked) {
+    pmx_set_error("weighted likelihood needs the tiled layout of Y and W");
+    return PMX_ERR_UNSUPPORTED;
+  }
+  pl->W = W;
   return PMX_OK;
 }
 
@@ -1112,7 +1152,7 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
   p.M = pl->M; p.N = pl->N; p.K = pl->K;
   p.NS = pl->Np / TILE_N;
   p.total_tiles = (long long)(pl->Mp / TILE_M) * p.NS;
-  p.Y = pl->Y; p.ldY = pl->ldY;
+  p.Y = pl->Y; p.W = pl->W; p.ldY = pl->ldY;
   p.GA = GA; p.GS = GS; p.loss = loss; p.done = done;
   p.want_ga = want_ga ? 1 : 0; p.want_gs = want_gs ? 1 : 0;
   p.ga_epoch = ga_epoch; p.ga_stride = (long long)ga_stride; p.gs_stride = (long long)gs_stride;
@@ -1149,7 +1189,12 @@ int launch_grad_umma(pmx_ctx* ctx, UmmaPlan* pl, const float* A, const float* S,
     // instantiations: k-halves (K <= 64 / K <= 128) x with / without the loss reduction x production / debug
     // (timing ablations + trace)
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
-    if (pl->KH == 1) {
+    if (pl->W) {   // weighted likelihood (production instantiations only)
+      auto kern = pl->KH == 1 ? (loss ? k_grad_umma<1, true, false, true> : k_grad_umma<1, false, false, true>)
+                              : (loss ? k_grad_umma<2, true, false, true> : k_grad_umma<2, false, false, true>);
+      kern<<<grid, NUM_THREADS, pl->KH == 1 ? SmemMap<1>::BYTES : SmemMap<2>::BYTES, ctx->stream>>>(pl->tmAhi, pl->tmAlo, pl->tmShi,
+                                                                                                 pl->tmSlo, p);
+    } else if (pl->KH == 1) {
       auto kern = dbg ? (loss ? k_grad_umma<1, true, true> : k_grad_umma<1, false, true>)
                       : (loss ? k_grad_umma<1, true, false> : k_grad_umma<1, false, false>);
       kern<<<grid, NUM_THREADS, SmemMap<1>::BYTES, ctx->stream>>>(pl->tmAhi, pl->tmAlo, pl->tmShi, pl->tmSlo, p);

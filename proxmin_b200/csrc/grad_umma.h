@@ -21,6 +21,9 @@ __host__ __device__ inline size_t pmx_y_index(int m, int n, int ldY, int y_block
   return ((((size_t)(m >> 7) * ldY + (n >> 7)) * 32 + ((m & 127) >> 2)) * 128 + (n & 127)) * 4 + (m & 3);
 }
 void umma_plan_destroy(pmx_ctx* ctx, UmmaPlan* plan);
+// weights of the weighted likelihood (nmf.py:25, 40): M x N in the tiled layout of Y (y_blocked = 1 plans only), or
+// nullptr for W = 1
+int umma_plan_set_W(UmmaPlan* plan, const float* W);
 // skip_split != 0: the plan's bf16 (hi, lo) operand buffers already hold the split of (A, S) -- the fused update
 // kernels wrote them -- so the two split passes are skipped
 // ga_epoch != nullptr (sharded runs over peer memory): GA is the base of a pair of buffers ga_stride elements apart

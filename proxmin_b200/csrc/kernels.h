@@ -19,7 +19,7 @@ int launch_lambda_max2(pmx_ctx* ctx, cudaStream_t st, const double* gram0, int w
 // tiled device copy (grad_umma.h); m0 is a multiple of 4
 int launch_y_interleave(pmx_ctx* ctx, cudaStream_t st, const float* stage, int pitch, int nrows, int ncols, float* Yb, int ldY,
                         int m0, int col0);
-int launch_grad_simt(pmx_ctx* ctx, const float* Y, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
+int launch_grad_simt(pmx_ctx* ctx, const float* Y, const float* W, int ldY, int y_blocked, const float* A, const float* S, int M, int N, int K, float* GA,
                      float* GS, double* loss, const int* done);
 
 // solver_kernels.cu

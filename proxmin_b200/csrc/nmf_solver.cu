@@ -28,6 +28,7 @@ struct pmx_nmf {
   pmx_ctx* ctx;
   int M, N, K;   // N = local number of columns (this rank's stripe of Y and S)
   double N_global; // total number of columns over all ranks (row means of S in step_adaprox)
+  float* W;      // weights of the weighted likelihood (nmf.py:25, 40) in the layout of Y, or nullptr (W = 1)
   int ldY;       // the device copy of Y is tiled (grad_umma.h): ldY = 128-column tiles per row block = ceil(N / 128)
   float *Y, *A, *S, *A_old, *S_old, *Ae, *Se, *GA, *GS;
   double *gramA, *gramS;
@@ -129,12 +130,13 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
       return PMX_ERR_UNSUPPORTED;
     }
     if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan, 1));
+    PMX_CHECK(umma_plan_set_W(h->plan, h->W));
     const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
     PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride, want));
     h->used_umma = true;
   } else {
     h->used_umma = false;
-    PMX_CHECK(launch_grad_simt(ctx, h->Y, h->ldY, 1, A, S, h->M, h->N, h->K, GA, GS, loss, done));
+    PMX_CHECK(launch_grad_simt(ctx, h->Y, h->W, h->ldY, 1, A, S, h->M, h->N, h->K, GA, GS, loss, done));
   }
   if (ctx->world > 1) {
     if (!defer_reduce && (want & 1) && GA) PMX_CHECK(pmx_comm_allreduce_internal(ctx, GA, (size_t)h->M * h->K, 0, ctx->stream));
@@ -254,7 +256,7 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   cudaStreamSynchronize(h->ctx->stream);
   cudaStreamSynchronize(h->ctx->aux);
   if (h->gram_part) pmx_dev_free(h->ctx, h->gram_part);
-  float* bufs[] = {h->Y, h->A, h->S, h->A_old, h->S_old, h->Ae, h->Se, h->GA, h->GS, h->MA, h->MS, h->VA, h->VS,
+  float* bufs[] = {h->Y, h->W, h->A, h->S, h->A_old, h->S_old, h->Ae, h->Se, h->GA, h->GS, h->MA, h->MS, h->VA, h->VS,
                    h->VhA, h->VhS, h->Psi, h->Z0, h->Z1, h->alphaA, h->alphaS};
   for (float* b : bufs)
     if (b) pmx_dev_free(h->ctx, b);
@@ -280,8 +282,7 @@ int pmx_nmf_destroy(pmx_nmf* h) {
   return PMX_OK;
 }
 
-int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncols) {
-  PMX_REQUIRE(h && host_Y, "NULL argument");
+static int upload_tiled(pmx_nmf* h, float* dst, const float* host_Y, size_t ld, int col0, int ncols) {
   PMX_REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= h->N, "column range outside the local stripe");
   if (ncols == 0) return PMX_OK;
   // The device copy is tiled (grad_umma.h).  Row chunks travel through two row-major staging buffers:
@@ -312,11 +313,11 @@ int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncol
     if (e == cudaSuccess) e = cudaEventRecord(copied[b], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux, copied[b], 0);
     if (e != cudaSuccess) {
-      pmx_set_error("pmx_nmf_set_Y: %s", cudaGetErrorString(e));
+      pmx_set_error("pmx_nmf_set_Y / set_W: %s", cudaGetErrorString(e));
       st = PMX_ERR_CUDA;
       break;
     }
-    st = launch_y_interleave(ctx, ctx->aux, stage[b], (int)pitch, (int)nr, ncols, h->Y, h->ldY, (int)m0, col0);
+    st = launch_y_interleave(ctx, ctx->aux, stage[b], (int)pitch, (int)nr, ncols, dst, h->ldY, (int)m0, col0);
     if (st == PMX_OK && cudaEventRecord(used[b], ctx->aux) != cudaSuccess) st = PMX_ERR_CUDA;
   }
   cudaStreamSynchronize(ctx->stream);
@@ -328,6 +329,36 @@ int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncol
   pmx_dev_free(ctx, stage[0]);
   pmx_dev_free(ctx, stage[1]);
   return st;
+}
+
+int pmx_nmf_set_Y(pmx_nmf* h, const float* host_Y, size_t ld, int col0, int ncols) {
+  PMX_REQUIRE(h && host_Y, "NULL argument");
+  return upload_tiled(h, h->Y, host_Y, ld, col0, ncols);
+}
+
+int pmx_nmf_set_W(pmx_nmf* h, const float* host_W, size_t ld, int col0, int ncols) {
+  PMX_REQUIRE(h && host_W, "NULL argument");
+  if (!h->W) {
+    const size_t n = (size_t)pmx_div_up(h->M, 128) * h->ldY * 16384;
+    PMX_CHECK(alloc_f(h->ctx, &h->W, n));
+    PMX_CUDA(cudaMemsetAsync(h->W, 0, sizeof(float) * n, h->ctx->stream));
+    if (h->plan) PMX_CHECK(umma_plan_set_W(h->plan, h->W));
+  }
+  return upload_tiled(h, h->W, host_W, ld, col0, ncols);
+}
+
+int pmx_nmf_gradient(pmx_nmf* h, double* loss_host_or_null) {
+  PMX_REQUIRE(h != nullptr, "NULL argument");
+  h->tail_G_pending = false;
+  double* dl = loss_host_or_null ? &h->ctl->norms[6] : nullptr;
+  PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, dl, 0, nullptr));
+  if (loss_host_or_null) {
+    PMX_CHECK(pull_ctl(h));
+    *loss_host_or_null = h->h_ctl->norms[6];
+  } else {
+    PMX_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  }
+  return PMX_OK;
 }
 
 static int which_ptr(pmx_nmf* h, int which, float** p, size_t* n) {
@@ -492,6 +523,7 @@ static int tail_prologue(pmx_nmf* h) {
   pmx_ctx* ctx = h->ctx;
   const int* done = &h->ctl->done;
   if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan, 1));
+  PMX_CHECK(umma_plan_set_W(h->plan, h->W));
   if (ctx->world > 1) {
     char* loc = static_cast<char*>(ctx->peer_arena.local);
     PMX_CHECK(umma_plan_use_A(h->plan, loc + h->off_Ahi, loc + h->off_Alo));
@@ -1130,7 +1162,7 @@ int pmx_nmf_grad(pmx_ctx* ctx, const float* Y, const float* A, const float* S, i
     umma_plan_destroy(ctx, plan);
     return st;
   }
-  return launch_grad_simt(ctx, Y, N, 0, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);
+  return launch_grad_simt(ctx, Y, nullptr, N, 0, A, S, M, N, K, G_A, G_S, loss_or_null, nullptr);
 }
 
 int pmx_nmf_lipschitz(pmx_ctx* ctx, const float* A, const float* S, int M, int N, int K, float* lip_A_host,
@@ -1138,13 +1170,14 @@ int pmx_nmf_lipschitz(pmx_ctx* ctx, const float* A, const float* S, int M, int N
   PMX_REQUIRE(ctx && A && S, "NULL argument");
   double* gram;
   pmx_ctl* ctl;
-  PMX_CUDA(cudaMalloc((void**)&gram, sizeof(double) * K * K * 2));
+  const size_t kk2 = ((size_t)K * K + 1) & ~(size_t)1;   // the second Gram starts 16-byte aligned (vector zero-fill)
+  PMX_CUDA(cudaMalloc((void**)&gram, sizeof(double) * kk2 * 2));
   PMX_CUDA(cudaMalloc((void**)&ctl, sizeof(pmx_ctl)));
   PMX_CUDA(cudaMemsetAsync(ctl, 0, sizeof(pmx_ctl), ctx->stream));
   int st = launch_gram(ctx, ctx->stream, S, K, N, false, gram, nullptr);
   if (st == PMX_OK) st = launch_lambda_max(ctx, ctx->stream, gram, K, ctl, 0);
-  if (st == PMX_OK) st = launch_gram(ctx, ctx->stream, A, M, K, true, gram + (size_t)K * K, nullptr);
-  if (st == PMX_OK) st = launch_lambda_max(ctx, ctx->stream, gram + (size_t)K * K, K, ctl, 1);
+  if (st == PMX_OK) st = launch_gram(ctx, ctx->stream, A, M, K, true, gram + kk2, nullptr);
+  if (st == PMX_OK) st = launch_lambda_max(ctx, ctx->stream, gram + kk2, K, ctl, 1);
   pmx_ctl hc;
   memset(&hc, 0, sizeof(hc));
   if (st == PMX_OK) {

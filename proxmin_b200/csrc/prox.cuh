@@ -47,6 +47,29 @@ static inline int chain_unity_axis(const ProxChain& c) {  // -1 none, 0/1 the si
   return ax;
 }
 
+// Principal branch of the Lambert W function for real z >= 0 (scipy.special.lambertw of operators.py:183, whose
+// argument here is always a positive real): Halley iterations in fp64 from log1p(z) / the asymptotic series.
+__device__ inline double pmx_lambertw0(double z) {
+  if (!(z > 0.0)) return z;                 // 0 -> 0, NaN -> NaN
+  if (isinf(z)) return z;
+  double w;
+  if (z < 2.718281828459045) {
+    w = log1p(z);
+    w = w - (w * exp(w) - z) / (exp(w) * (w + 1.0));   // one Newton step: log1p overshoots for z ~ 1
+  } else {
+    const double l1 = log(z), l2 = log(l1);
+    w = l1 - l2 + l2 / l1;
+  }
+  for (int it = 0; it < 8; ++it) {
+    const double ew = exp(w), f = w * ew - z;
+    const double wp1 = w + 1.0;
+    const double dw = f / (ew * wp1 - (w + 2.0) * f / (2.0 * wp1));
+    w -= dw;
+    if (fabs(dw) <= 1e-16 * fabs(w)) break;
+  }
+  return w;
+}
+
 // One elementwise primitive.  The comparisons are written exactly like the NumPy masks of
 // the reference so that NaN, +-inf and -0.0 behave identically (support sets are bit-exact).
 __device__ __forceinline__ float prox_elem(float x, int op, float t) {
@@ -61,6 +84,27 @@ __device__ __forceinline__ float prox_elem(float x, int op, float t) {
       a = (a < 0.0f) ? 0.0f : a;                                      // prox_plus of |X|-t
       float s = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : ((x == 0.0f) ? 0.0f : x));  // np.sign
       return s * a;
+    }
+    case PMX_OP_MAXENT: {                                             // operators.py:182-183
+      if (!(x > 0.0f)) return x;                                      // only X[X > 0] is touched
+      // NumPy evaluates  gamma_ * real(lambertw(exp(X / gamma_ - 1) / gamma_))  with the fp32 array X: the argument of
+      // lambertw is an fp32 value (np.exp of an fp32 array), W and the product with gamma_ are fp64, the assignment
+      // rounds to fp32
+      const float a = __fsub_rn(__fdiv_rn(x, t), 1.0f);
+      const float e = (float)exp((double)a);
+      const float z = __fdiv_rn(e, t);
+      return (float)((double)t * pmx_lambertw0((double)z));
+    }
+    case PMX_OP_MAXENT64: {                                           // same, caller's array is float64
+      if (!(x > 0.0f)) return x;
+      const double a = (double)x / (double)t - 1.0;
+      if (a < 700.0) return (float)((double)t * pmx_lambertw0(exp(a) / (double)t));
+      // exp(a) overflows even in fp64 (the reference returns inf there as well only beyond a = 709): solve
+      // w + log(w) = a - log(t) directly
+      const double Lr = a - log((double)t);
+      double w = Lr - log(Lr);
+      for (int it = 0; it < 6; ++it) w -= (w + log(w) - Lr) / (1.0 + 1.0 / w);
+      return a > 709.78 ? __int_as_float(0x7f800000) : (float)((double)t * w);
     }
     default: return x;
   }

@@ -28,7 +28,7 @@ logger = logging.getLogger("proxmin")
 class Problem(object):
     """Device-resident (Y, A, S) plus solver state; thin wrapper over ``pmx_nmf``."""
 
-    def __init__(self, Y, A, S, ctx=None):
+    def __init__(self, Y, A, S, ctx=None, W=None):
         Y = np.asarray(Y)
         M, N = Y.shape
         K = A.shape[1]
@@ -38,17 +38,33 @@ class Problem(object):
         self.handle = C.c_void_p()
         L = _ffi.lib()
         _ffi.check(L.pmx_nmf_create(self.ctx.handle, M, N, K, C.byref(self.handle)))
-        # upload Y in column blocks (fp32 staging of at most ~256 MB for fp64 / non-contiguous input)
-        if Y.dtype == np.float32 and Y.flags.c_contiguous:
-            _ffi.check(L.pmx_nmf_set_Y(self.handle, Y.ctypes.data_as(C.c_void_p), N, 0, N))
-        else:
-            blk = max(1, (1 << 26) // max(M, 1))
-            for c0 in range(0, N, blk):
-                c1 = min(N, c0 + blk)
-                part = np.ascontiguousarray(Y[:, c0:c1], dtype=np.float32)
-                _ffi.check(L.pmx_nmf_set_Y(self.handle, part.ctypes.data_as(C.c_void_p), c1 - c0, c0, c1 - c0))
+        self._upload_matrix(Y, L.pmx_nmf_set_Y)
+        if W is not None:   # weighted likelihood (nmf.py:25, 40): an M x N matrix next to Y
+            W = np.asarray(W)
+            assert W.shape == (M, N), "W must have the shape of Y"
+            self._upload_matrix(W, L.pmx_nmf_set_W)
         self.set(_ffi.A, A)
         self.set(_ffi.S, S)
+
+    def _upload_matrix(self, Y, setter):
+        """M x N host matrix -> tiled device copy, in column blocks (fp32 staging of at most ~256 MB for fp64 /
+        non-contiguous input)."""
+        M, N = Y.shape
+        if Y.dtype == np.float32 and Y.flags.c_contiguous:
+            _ffi.check(setter(self.handle, Y.ctypes.data_as(C.c_void_p), N, 0, N))
+            return
+        blk = max(1, (1 << 26) // max(M, 1))
+        for c0 in range(0, N, blk):
+            c1 = min(N, c0 + blk)
+            part = np.ascontiguousarray(Y[:, c0:c1], dtype=np.float32)
+            _ffi.check(setter(self.handle, part.ctypes.data_as(C.c_void_p), c1 - c0, c0, c1 - c0))
+
+    def gradient(self, want_loss=False):
+        """Gradients of the likelihood at the current factors into the GA / GS buffers (nmf.py:28-41); returns the
+        log-likelihood (nmf.py:13-25) when asked for."""
+        loss = C.c_double(0)
+        _ffi.check(_ffi.lib().pmx_nmf_gradient(self.handle, C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
 
     def close(self):
         if self.handle:
@@ -152,10 +168,13 @@ class Problem(object):
 
 
 def _check_W(W):
-    if np.ndim(W) != 0 or W != 1:
-        raise NotImplementedError(
-            "weighted likelihood (array W) is outside the B200 hot path of this release "
-            "(the reference's own weighted step_pgm is broken, SURVEY.md section 2 row 1)")
+    """Scalar W == 1 -> None; an M x N weight matrix is returned as it is.  Other scalars are not part of the
+    reference's contract (its docstring asks for an M x N matrix)."""
+    if np.ndim(W) == 0:
+        if W == 1:
+            return None
+        raise NotImplementedError("scalar weights other than 1: pass an M x N weight matrix (nmf.py:19)")
+    return np.asarray(W)
 
 
 def _device_triplet(A, S, Y):
@@ -171,9 +190,9 @@ def _device_triplet(A, S, Y):
 
 def log_likelihood(*X, Y=0, W=1):
     """sum(W (Y - A S)^2) / 2 (nmf.py:13-25), one fused residual pass on the device."""
-    _check_W(W)
+    Wm = _check_W(W)
     A, S = X
-    prob = Problem(Y, A, S)
+    prob = Problem(Y, A, S, W=Wm)
     try:
         v = prob.loss()
     finally:
@@ -182,9 +201,17 @@ def log_likelihood(*X, Y=0, W=1):
 
 
 def grad_likelihood(*X, Y=0, W=1):
-    """(D S^T, A^T D) with D = A S - Y (nmf.py:28-41), one pass over Y, no M x N temporary."""
-    _check_W(W)
+    """(D S^T, A^T D) with D = W (A S - Y) (nmf.py:28-41), one pass over Y (and W), no M x N temporary."""
+    Wm = _check_W(W)
     A, S = X
+    dt = np.result_type(A.dtype, S.dtype)
+    if Wm is not None:
+        prob = Problem(Y, A, S, W=Wm)
+        try:
+            prob.gradient()
+            return prob.get(_ffi.GA, dtype=dt), prob.get(_ffi.GS, dtype=dt)
+        finally:
+            prob.close()
     ctx, A32, S32, Y32, M, N, K = _device_triplet(A, S, Y)
     dY, dA, dS = ctx.upload(Y32), ctx.upload(A32), ctx.upload(S32)
     dGA, dGS = ctx.malloc(4 * M * K), ctx.malloc(4 * K * N)
@@ -196,7 +223,6 @@ def grad_likelihood(*X, Y=0, W=1):
     finally:
         for p in (dY, dA, dS, dGA, dGS):
             ctx.free(p)
-    dt = np.result_type(A.dtype, S.dtype)
     return GA.astype(dt, copy=False), GS.astype(dt, copy=False)
 
 
@@ -228,8 +254,13 @@ def step_S(A, S):
 
 
 def step_pgm(*X, it=None, W=1):
-    """Lipschitz step sizes for both factors (nmf.py:52-65, W == 1 branch)."""
-    _check_W(W)
+    """Lipschitz step sizes for both factors (nmf.py:52-65, W == 1 branch).  With a weight matrix the reference
+    evaluates ``if W == 1`` on an array and raises ValueError (nmf.py:63); the same statement raises it here.  (Its
+    weighted branch builds M*N x M*K sparse operators and is not reachable; weighted PGM needs a user ``step``.)"""
+    if W == 1:
+        pass
+    else:
+        raise NotImplementedError("weighted step_pgm (sparse eigs branch, nmf.py:66-88) is outside the B200 hot path")
     A, S = X
     la, ls = _lipschitz(A, S)
     return 1 / la, 1 / ls

@@ -33,7 +33,7 @@ def _apply(X, step, ops):
     # thresholds of type="relative" follow NumPy's scalar arithmetic of the reference (operators.py:4-14)
     res = []
     for (o, rel, a, t) in ops:
-        if rel and o in (_ffi.OP_MIN, _ffi.OP_MAX, _ffi.OP_HARD, _ffi.OP_SOFT):
+        if rel and o in (_ffi.OP_MIN, _ffi.OP_MAX, _ffi.OP_HARD, _ffi.OP_SOFT, _ffi.OP_MAXENT, _ffi.OP_MAXENT64):
             if np.ndim(step) != 0:
                 raise NotImplementedError("array-valued step with a relative threshold")
             t = np.float32(t * step)
@@ -119,6 +119,20 @@ def prox_soft_plus(X, step, thresh=0, type="relative"):
     return _apply(X, step, [(_ffi.OP_SOFT, _rel(type), 0, thresh), (_ffi.OP_PLUS, 0, 0, 0.0)])
 
 
+def prox_max_entropy(X, step, gamma=1, type="relative"):
+    """Proximal operator of g(x) = gamma sum_i x_i ln(x_i) (operators.py:163-184):
+    X[X > 0] = gamma_ W(exp(X / gamma_ - 1) / gamma_) with the Lambert W function evaluated on the device
+    (Halley iterations in fp64, like scipy's lambertw it replaces); elements <= 0 are left untouched."""
+    op = _ffi.OP_MAXENT64 if isinstance(X, np.ndarray) and X.dtype == np.float64 else _ffi.OP_MAXENT
+    return _apply(X, step, [(op, _rel(type), 0, gamma)])
+
+
+def prox_components(X, step, prox=None, axis=0):
+    """operators.py:87-106.  Dead code in the reference: its body reads the undefined name ``prox_list`` and raises
+    NameError on every call; the same exception is raised here."""
+    raise NameError("name 'prox_list' is not defined")
+
+
 class AlternatingProjections(object):
     """Sequential composition of proximal operators (operators.py:187-224): the list is applied in
     reverse order, ``repeat`` times.  When every member is a built-in, the whole composition is one
@@ -194,6 +208,12 @@ def describe(prox):
             return None
         pre = [(_ffi.OP_PLUS, 0, 0, 0.0)] if fn is prox_unity_plus else []
         return pre + [(_ffi.OP_UNITY, 0, axis, 0.0)]
+    if fn is prox_max_entropy:
+        gamma = kw.pop("gamma", 1)
+        type_ = kw.pop("type", "relative")
+        if kw or type_ not in ("relative", "absolute") or np.ndim(gamma) != 0:
+            return None
+        return [(_ffi.OP_MAXENT, type_ == "relative", 0, float(gamma))]
     table = _builtin_table()
     if fn in table:
         thresh = kw.pop("thresh", 0)

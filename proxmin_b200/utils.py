@@ -60,31 +60,63 @@ class NesterovAccelerator(object):
 
 
 def get_spectral_norm(L):
-    """Squared spectral norm of a dense matrix = lambda_max(L^T L) (utils.py:14-35, dense branch),
-    computed on the device (Gram kernel + one-CTA eigen-solver)."""
+    """Squared spectral norm of a dense matrix = lambda_max(L^T L) (utils.py:14-35, dense branch), on the device:
+    Gram kernel + one-CTA eigen-solver on the smaller of L^T L / L L^T when that is at most 128 x 128, power iteration
+    with device matrix-vector products otherwise."""
     if L is None:
         return 1
-    if hasattr(L, "spectral_norm"):
-        return L.spectral_norm
+    if isinstance(L, MatrixAdapter):
+        if L.L is None:
+            return 1
+        if L._spec_norm is not None:
+            return L._spec_norm
+        adapter, L = L, L.L
+    else:
+        adapter = None
+    import scipy.sparse
+    if scipy.sparse.issparse(L):
+        raise NotImplementedError("sparse linear operators are outside the B200 hot path")
     L = np.asarray(L)
     if L.ndim != 2:
         raise ValueError("get_spectral_norm expects a matrix")
-    import scipy.sparse  # noqa: F401  (kept lazy: only to reject sparse input explicitly)
-    if scipy.sparse.issparse(L):
-        raise NotImplementedError("sparse linear operators are outside the B200 hot path")
-    ctx = _ffi.context()
-    M, K = L.shape
-    if K > 128:
-        raise NotImplementedError("get_spectral_norm: more than 128 columns")
-    dA = ctx.upload(L)
-    dS = ctx.upload(np.zeros((K, 4), np.float32))
-    try:
-        lipA, lipS = C.c_float(0), C.c_float(0)
-        _ffi.check(_ffi.lib().pmx_nmf_lipschitz(ctx.handle, dA, dS, M, 4, K, C.byref(lipA), C.byref(lipS)))
-    finally:
-        ctx.free(dA)
-        ctx.free(dS)
-    return L.dtype.type(lipS.value) if L.dtype.kind == "f" else lipS.value
+    dt = L.dtype.type if L.dtype.kind == "f" else np.float64
+    Ls = L if L.shape[1] <= L.shape[0] else L.T       # the nonzero spectra of L^T L and L L^T agree
+    M, K = Ls.shape
+    if K <= 128:
+        ctx = _ffi.context()
+        dA = ctx.upload(np.ascontiguousarray(Ls, dtype=np.float32))
+        dS = ctx.upload(np.zeros((K, 4), np.float32))
+        try:
+            lipA, lipS = C.c_float(0), C.c_float(0)
+            _ffi.check(_ffi.lib().pmx_nmf_lipschitz(ctx.handle, dA, dS, M, 4, K, C.byref(lipA), C.byref(lipS)))
+        finally:
+            ctx.free(dA)
+            ctx.free(dS)
+        return dt(lipS.value)
+    from . import _dev
+
+    dm = adapter._device() if adapter is not None else _dev.DeviceMatrix(L)
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(dm.shape[1]).astype(np.float32)
+    v /= np.sqrt(_dev.sumsq(v))
+    lam = 0.0
+    for it in range(2000):
+        w = dm.Tdot(dm.dot(v))
+        nw = np.sqrt(_dev.sumsq(w))
+        if not np.isfinite(nw):
+            raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
+        if nw == 0:
+            lam = 0.0
+            break
+        new = nw                       # |L^T L v| -> lambda_max for a unit vector v
+        v = (w / np.float32(nw)).astype(np.float32)
+        if it > 4 and abs(new - lam) <= 1e-7 * new:
+            lam = new
+            break
+        lam = new
+    if adapter is None:
+        dm.close()
+    return dt(lam)
 
 
 def l2sq(x):
@@ -150,6 +182,140 @@ class ApproximateCache(object):
         else:
             self.it += 1
         return self.stored
+
+
+class BarzilaiBorweinStepper:
+    """Barzilai-Borwein step sizes, stabilised after Burdakov et al. (arXiv:1907.06409, Algorithm 2.1)
+    (utils.py:209-241).  ``stepper.step`` is a ``step(*X, it=None, grads=None)`` callable for ``pgm``; every
+    reduction (sum S^2, sum S Y, sum Y^2, sum G^2, max|X|, max|G|) is one device kernel per block
+    (``pmx_ew`` opcodes BB / MAXABS), the remaining arithmetic is a handful of host scalars."""
+
+    def __init__(self, type=1, init_r=0.1):
+        assert type in [1, 2]
+        self.r = init_r
+        self.type = type
+
+    def step(self, *X, it=None, grads=None):
+        from . import _dev
+
+        N = len(X)
+        if it == 0:
+            self.Delta = np.array([np.inf, ] * N)
+            self.X_ = _copy_tuple(X)
+            self.G_ = grads  # no copy needed, created fresh every single iteration
+            return tuple(self.r * _dev.maxabs(X[j]) / _dev.maxabs(grads[j]) for j in range(N))
+
+        G = grads
+        red = [_dev.bb_sums(X[j], self.X_[j], G[j], self.G_[j]) for j in range(N)]   # (S.S, S.Y, Y.Y, G.G)
+        dt = [np.result_type(X[j].dtype, np.float32).type for j in range(N)]
+        self.X_ = _copy_tuple(X)
+        self.G_ = grads
+
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if self.type == 1:
+                A = tuple(dt[j](red[j][0]) / dt[j](red[j][1]) for j in range(N))
+            else:
+                A = tuple(dt[j](red[j][1]) / dt[j](red[j][2]) for j in range(N))
+            if it <= 3:
+                self.Delta = np.minimum(self.Delta, tuple(np.sqrt(dt[j](red[j][0])) for j in range(N)))
+            Astab = tuple(self.Delta[j] / np.sqrt(dt[j](red[j][3])) for j in range(N))
+        return np.minimum(np.abs(A), Astab)
+
+
+class MatrixAdapter(object):
+    """Linear operator wrapper that tolerates ``None`` (= identity) and caches the spectral norm (utils.py:38-101).
+    A dense matrix is uploaded once and stays resident on the device; ``dot`` is one device GEMM per call
+    (``pmx_matmul``), ``.T`` shares the device copy.  With ``L is None`` the argument of ``dot`` is returned uncopied,
+    as in the reference (utils.py:70-74).  scipy.sparse operators are outside the B200 hot path."""
+
+    def __init__(self, L, axis=None, _dm=None, _trans=False):
+        spec_norm = None
+        while isinstance(L, MatrixAdapter):   # prevent cascade
+            spec_norm = L._spec_norm
+            axis = L.axis
+            _dm, _trans = L._dm, L._trans
+            L = L.L
+        if L is not None:
+            import scipy.sparse
+            if scipy.sparse.issparse(L):
+                raise NotImplementedError("sparse linear operators are outside the B200 hot path")
+            L = np.asarray(L)
+        self.L = L
+        self.axis = axis
+        self._spec_norm = spec_norm
+        self._dm, self._trans = _dm, _trans
+
+    def _device(self):
+        from . import _dev
+
+        if self._dm is None:
+            self._dm = _dev.DeviceMatrix(self.L)
+            self._trans = False
+        return self._dm
+
+    @property
+    def spectral_norm(self):
+        if self._spec_norm is None:
+            if self.L is not None:
+                self._spec_norm = get_spectral_norm(self)
+            else:
+                self._spec_norm = 1
+        return self._spec_norm
+
+    @property
+    def T(self):
+        if self.L is None:
+            return self  # NOT: self.L !!!
+        # because we need to preserve axis for dot(), create a new adapter (it shares the device copy)
+        self._device()
+        out = MatrixAdapter(self.L.T, axis=self.axis, _dm=self._dm, _trans=not self._trans)
+        out._spec_norm = self._spec_norm   # lambda_max(L^T L) = lambda_max(L L^T)
+        return out
+
+    def _mul(self, X):
+        dm = self._device()
+        return dm.Tdot(X) if self._trans else dm.dot(X)
+
+    def dot(self, X):
+        if self.L is None:
+            # CAVEAT (reference): not a copy
+            return X
+        if self.axis is None:
+            return self._mul(X)
+        if self.axis == 1:
+            return self._mul(X.reshape(-1)).reshape(X.shape[0], -1)
+        raise NotImplementedError(
+            "MatrixAdapter.dot() is not useful with axis=0.\n"
+            "Use regular matrix dot product instead!"
+        )
+
+    def __len__(self):
+        return len(self.L)
+
+    @property
+    def shape(self):
+        return self.L.shape
+
+    @property
+    def size(self):
+        return self.L.size
+
+    @property
+    def ndim(self):
+        return self.L.ndim
+
+
+def initZU(X, L):
+    """Z = L X, U = 0 per constraint (utils.py:244-254)."""
+    if not isinstance(L, list):
+        Z = L.dot(X).copy()
+        U = np.zeros(Z.shape, dtype=Z.dtype)
+    else:
+        Z, U = [], []
+        for i in range(len(L)):
+            Z.append(L[i].dot(X).copy())
+            U.append(np.zeros(Z[i].shape, dtype=Z[i].dtype))
+    return Z, U
 
 
 class ConstantStep(object):

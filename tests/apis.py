@@ -93,14 +93,12 @@ def oracle():
         return c, M, V, Vh
 
     def admm(X, prox_f, step_f, prox_g=None, step_g=None, L=None, **k):
-        assert L is None
-        c, e, n = o.admm(X, prox_f, step_f, prox_g=prox_g, step_g=step_g, **k)
+        c, e, n = o.admm(X, prox_f, step_f, prox_g=prox_g, step_g=step_g, L=L, **k)
         state["last"] = (n, None)
         return c, e
 
     def sdmm(X, prox_f, step_f, proxs_g=None, steps_g=None, Ls=None, **k):
-        assert Ls is None
-        c, n = o.sdmm(X, prox_f, step_f, proxs_g=proxs_g, steps_g=steps_g, **k)
+        c, n = o.sdmm(X, prox_f, step_f, proxs_g=proxs_g, steps_g=steps_g, Ls=Ls, **k)
         state["last"] = (n, None)
         return c
 
@@ -138,7 +136,7 @@ def oracle():
         def __call__(self, *X, it=None):
             self.trace.append(tuple(x.copy() for x in X))
 
-    api.utils = types.SimpleNamespace(Traceback=Traceback)
+    api.utils = types.SimpleNamespace(Traceback=Traceback, BarzilaiBorweinStepper=o.BarzilaiBorweinStepper)
     return api
 
 

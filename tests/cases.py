@@ -427,3 +427,132 @@ def sdmm_lasso_plus(api):
     conv = api.sdmm(X, prox_f, step_f, proxs_g=[prox_g, api.prox_plus], max_iter=100, e_rel=1e-5)
     n, _ = api.iterations()
     return {"X": X, "converged": np.bool_(conv), "iterations": np.int64(n)}
+
+
+# --------------------------------------------------------------------------
+# prox_max_entropy, BarzilaiBorweinStepper, non-identity L, weighted likelihood
+# --------------------------------------------------------------------------
+
+@case
+def operators_max_entropy(api):
+    """operators.py:163-184: Lambert-W prox of gamma sum x ln x; only X > 0 is touched, exp overflows to inf in fp32
+    for X / gamma_ > 89 (the reference then returns inf)."""
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((5, 48)) * 2).astype(np.float32)
+    x[0, :8] = [0.0, -0.0, 1e-6, 0.5, 1.0, 7.5, 30.0, 60.0]
+    x[1, :3] = [np.nan, -np.inf, -3.0]
+    out = {}
+    with np.errstate(over="ignore", invalid="ignore"):
+        out["rel"] = np.array(api.prox_max_entropy(x.copy(), 0.5, gamma=1))
+        out["rel_small"] = np.array(api.prox_max_entropy(x.copy(), 0.25, gamma=0.3))
+        out["abs"] = np.array(api.prox_max_entropy(x.copy(), 0.5, gamma=2.0, type="absolute"))
+        x64 = x.astype(np.float64)
+        out["f64"] = np.array(api.prox_max_entropy(x64, 0.5, gamma=1))
+    return out
+
+
+@case
+def pgm_barzilai_borwein(api):
+    """utils.py:209-241: both BB step types through ``pgm``.  The stepper returns an ndarray from the second
+    iteration on, which ``pgm`` wraps as ONE step (utils.py:8-12): the reference supports it for a single
+    variable only -- non-negative least squares  min |Y - A S|^2 over S >= 0 with A fixed."""
+    out = {}
+    for typ in (1, 2):
+        Y, A, S = workloads.cfg1(48, 80, 4, seed=21)
+
+        def grad(S_):
+            return A.T.dot(A.dot(S_) - Y)
+
+        bb = api.utils.BarzilaiBorweinStepper(type=typ, init_r=0.1)
+        conv, G, st = api.pgm(S, grad, bb.step, prox=api.prox_plus, max_iter=25, e_rel=0)
+        out["S%d" % typ] = S
+        out["step%d" % typ] = np.asarray(st, dtype=np.float64).reshape(-1)
+    return out
+
+
+def _lasso_L(seed, p, n):
+    rng = np.random.default_rng(seed)
+    L = (rng.standard_normal((p, n)) / np.sqrt(n)).astype(np.float32)
+    xs = np.zeros(n, np.float32)
+    xs[rng.choice(n, n // 8, replace=False)] = (2 * rng.standard_normal(n // 8)).astype(np.float32)
+    b = (xs + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    return L, b
+
+
+@case
+def admm_dense_L(api):
+    """admm / sdmm / bsdmm with non-identity dense linear operators (utils.py:38-101, :295-346): generalised
+    LASSO  min 0.5 |x - b|^2 + lambda |L x|_1  and friends."""
+    out = {}
+    L, b = _lasso_L(31, 24, 40)
+
+    def prox_f(X, step):
+        return X - step * (X - b)
+
+    def step_f(X, it=None):
+        return np.float32(0.5)
+
+    X = np.zeros(40, np.float32)
+    conv, err = api.admm(X, prox_f, step_f, prox_g=partial(api.prox_soft, thresh=0.1), L=L, max_iter=60, e_rel=1e-4)
+    out["admm_X"], out["admm_err"] = X, np.asarray(err, dtype=np.float64)
+    out["admm_it"] = np.int64(api.iterations()[0])
+
+    L2, _ = _lasso_L(32, 40, 40)
+    X = np.zeros(40, np.float32)
+    api.sdmm(X, prox_f, step_f, proxs_g=[partial(api.prox_soft, thresh=0.1), api.prox_plus], Ls=[L, None],
+             max_iter=60, e_rel=1e-4)
+    out["sdmm_X"] = X
+    out["sdmm_it"] = np.int64(api.iterations()[0])
+
+    rng = np.random.default_rng(33)
+    b1 = rng.standard_normal(20).astype(np.float32)
+    b2 = rng.standard_normal((6, 5)).astype(np.float32)
+    bb = [b1, b2]
+    L1 = (rng.standard_normal((12, 20)) / 4).astype(np.float32)
+    L3 = (rng.standard_normal((6, 6)) / 2).astype(np.float32)
+
+    def proxs_f(X, step, Xs=None, j=None):
+        return X - step * (X - bb[j])
+
+    def steps_f(Xs, j=None):
+        return np.float32(0.4)
+
+    X1, X2 = np.zeros(20, np.float32), np.zeros((6, 5), np.float32)
+    api.bsdmm([X1, X2], proxs_f, steps_f, proxs_g=[[partial(api.prox_soft, thresh=0.05)], [api.prox_plus, api.prox_plus]],
+              Ls=[[L1], [L3, None]], max_iter=40, e_rel=1e-4)
+    out["bsdmm_X1"], out["bsdmm_X2"] = X1, X2
+    out["bsdmm_it"] = np.int64(api.iterations()[0])
+    return out
+
+
+def _weights(shape, seed):
+    rng = np.random.default_rng(seed)
+    W = (0.25 + 0.75 * rng.random(shape)).astype(np.float32)
+    W[rng.random(shape) < 0.05] = 0.0        # masked entries
+    return W
+
+
+@case
+def nmf_weighted(api):
+    """Weighted likelihood (nmf.py:25, 40): gradient / loss with an M x N weight matrix, adaprox (whose default step
+    does not depend on W) and PGM with a user step (the reference's weighted step_pgm is broken)."""
+    out = {}
+    Y, A, S = workloads.cfg2(96, 224 + 40, 12, seed=41)
+    W = _weights(Y.shape, 42)
+    gA, gS = api.nmf.grad_likelihood(A, S, Y=Y, W=W)
+    out["G_A"], out["G_S"] = gA, gS
+    out["loss"] = np.float64(api.nmf.log_likelihood(A, S, Y=Y, W=W))
+
+    A1, S1 = A.copy(), S.copy()
+    api.nmf.nmf(Y, A1, S1, W=W, algorithm=api.adaprox, scheme="amsgrad", max_iter=30, check_convergence=False)
+    n, sub = api.iterations()
+    out["ada_A"], out["ada_S"] = A1, S1
+    out["ada_sub"] = np.array(sub, dtype=np.int64)
+
+    def step(*X, it=None):
+        return tuple(0.5 * s for s in api.nmf.step_pgm(*X))
+
+    A2, S2 = A.copy(), S.copy()
+    api.nmf.nmf(Y, A2, S2, W=W, step=step, prox_S=api.prox_unity_plus, max_iter=40, e_rel=0)
+    out["pgm_A"], out["pgm_S"] = A2, S2
+    return out

@@ -344,6 +344,96 @@ def test_sdmm_lasso(product):
     assert np.array_equal(X, want["X"])
 
 
+# ---------------------------------------------------------------- SURVEY 8-f rows
+def test_prox_max_entropy(product):
+    """operators.py:163-184 (Lambert W on the device in fp64, like scipy's).  Tolerance 2e-6 relative: the argument
+    of W is an fp32 exp whose last bit may differ between NumPy and CUDA; untouched elements (X <= 0, NaN) and the
+    fp32 overflow to inf are exact."""
+    want = load_golden("operators_max_entropy")
+    with np.errstate(over="ignore", invalid="ignore"):
+        got = cases.operators_max_entropy(product)
+    for k in want:
+        w, g = np.asarray(want[k]), np.asarray(got[k])
+        assert g.dtype == w.dtype, k
+        untouched = ~(w > 0) | ~np.isfinite(w)
+        assert np.array_equal(g[untouched], w[untouched], equal_nan=True), k + " (untouched / overflow)"
+        assert np.array_equal(np.signbit(g[untouched]), np.signbit(w[untouched])), k
+        # float64 arrays travel through fp32 device buffers (DESIGN.md: parity is defined on fp32 inputs)
+        assert np.allclose(g[~untouched], w[~untouched], rtol=2e-6 if k != "f64" else 3e-7 * 4, atol=0), k
+
+
+def test_barzilai_borwein_stepper(product):
+    """utils.py:209-241 through pgm: reductions on the device (fp32 products, fp64 accumulation vs NumPy's pairwise
+    fp32 sums): the 25-iteration path agrees to 2e-5 relative, the last step to 5e-3."""
+    want = load_golden("pgm_barzilai_borwein")
+    got = cases.pgm_barzilai_borwein(product)
+    for typ in (1, 2):
+        assert_close(got["S%d" % typ], want["S%d" % typ], 2e-5, "S%d" % typ)
+        assert_same_support(got["S%d" % typ], want["S%d" % typ], "S%d" % typ, guard=1e-4)
+        # the BB step is a ratio of sums over DIFFERENCES of consecutive iterates / gradients: fp32 rounding noise of
+        # the path is amplified ~100x in it
+        assert np.allclose(got["step%d" % typ], want["step%d" % typ], rtol=5e-3), typ
+
+
+def test_admm_family_dense_L(product):
+    """admm / sdmm / bsdmm with non-identity dense linear operators (utils.py:38-101, 295-391): L X, L^T (..) and the
+    spectral norm on the device.  fp32 GEMM summation order differs from OpenBLAS: 2e-5 relative on the iterates,
+    iteration counts equal."""
+    want = load_golden("admm_dense_L")
+    got = cases.admm_dense_L(product)
+    for k in ("admm_it", "sdmm_it", "bsdmm_it"):
+        assert int(got[k]) == int(want[k]), k
+    for k in ("admm_X", "sdmm_X", "bsdmm_X1", "bsdmm_X2"):
+        assert_close(got[k], want[k], 2e-5, k)
+    # (e_pri, e_dual, |R|, |S|): the residual norms at convergence are differences of nearly equal iterates
+    assert np.allclose(got["admm_err"][:2], want["admm_err"][:2], rtol=1e-4), "tolerances"
+    assert np.allclose(got["admm_err"][2:], want["admm_err"][2:], rtol=2e-2), "residual norms"
+
+
+def test_matrix_adapter(product):
+    """utils.MatrixAdapter: None is the identity (argument returned uncopied), dense dot / T.dot / spectral norm"""
+    import proxmin_b200 as pmx
+
+    rng = np.random.default_rng(5)
+    L = rng.standard_normal((37, 150)).astype(np.float32)
+    x = rng.standard_normal(150).astype(np.float32)
+    X2 = rng.standard_normal((150, 9)).astype(np.float32)
+    ad = pmx.utils.MatrixAdapter(L)
+    assert np.allclose(ad.dot(x), L.dot(x), rtol=2e-5, atol=2e-5)
+    assert np.allclose(ad.dot(X2), L.dot(X2), rtol=2e-5, atol=2e-5)
+    y = rng.standard_normal(37).astype(np.float32)
+    assert np.allclose(ad.T.dot(y), L.T.dot(y), rtol=2e-5, atol=2e-5)
+    lam = np.linalg.eigvalsh(L.astype(np.float64) @ L.astype(np.float64).T).max()
+    assert abs(float(ad.spectral_norm) - lam) <= 5e-6 * lam
+    big = rng.standard_normal((200, 300)).astype(np.float32)       # both dimensions > 128: power iteration
+    lam = np.linalg.eigvalsh(big.astype(np.float64) @ big.astype(np.float64).T).max()
+    assert abs(float(pmx.utils.get_spectral_norm(big)) - lam) <= 1e-4 * lam
+    ident = pmx.utils.MatrixAdapter(None)
+    assert ident.dot(x) is x and ident.T is ident and ident.spectral_norm == 1
+
+
+def test_nmf_weighted_likelihood(product):
+    """Weighted likelihood W (nmf.py:25, 40): gradient / loss, fused adaprox loop, PGM with a user step (callback
+    loop, Y and W resident on the device)"""
+    want = load_golden("nmf_weighted")
+    got = cases.nmf_weighted(product)
+    assert_close(got["G_A"], want["G_A"], 2e-5, "G_A")
+    assert_close(got["G_S"], want["G_S"], 2e-5, "G_S")
+    assert abs(float(got["loss"]) - float(want["loss"])) <= 2e-5 * abs(float(want["loss"]))
+    assert np.array_equal(got["ada_sub"], want["ada_sub"])
+    for k in ("ada_A", "ada_S", "pgm_A", "pgm_S"):
+        assert_close(got[k], want[k], 1e-4, k)
+        assert_same_support(got[k], want[k], k, guard=1e-4)
+    import proxmin_b200 as pmx
+    from proxmin_b200 import workloads
+    Y, A, S = workloads.cfg2(64, 128, 4, seed=1)
+    W = np.ones_like(Y)
+    with pytest.raises(ValueError):          # the reference's `if W == 1` on an array (nmf.py:63)
+        pmx.nmf.nmf(Y, A, S, W=W, max_iter=2)
+    with pytest.raises(ValueError):
+        pmx.nmf.nmf(Y, A, S, W=W, algorithm=pmx.bsdmm, max_iter=2)
+
+
 # ---------------------------------------------------------------- tcgen05 kernel vs the SIMT kernel
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 512, 8), (300, 1000, 20), (77, 204, 5), (1024, 2048, 64), (130, 333, 7),
                                    (257, 129, 33), (256, 512, 96), (300, 700, 128), (130, 333, 65), (1024, 2048, 128)])

@@ -90,8 +90,9 @@ def test_argument_validation_matches_reference():
         pmx.nmf.nmf(np.zeros((2, 2)), np.zeros((2, 1)), np.zeros((1, 2)), algorithm=pmx.admm)
     with pytest.raises(AssertionError):
         pmx.prox_soft(X, 1.0, type="bogus")
-    with pytest.raises(NotImplementedError):
-        pmx.admm(X, lambda x, s: x, lambda x, it=None: 1.0, L=np.eye(3))
+    import scipy.sparse
+    with pytest.raises(NotImplementedError):   # dense L runs on the device; sparse operators are out of scope
+        pmx.admm(X, lambda x, s: x, lambda x, it=None: 1.0, L=scipy.sparse.eye(3))
 
 
 REF = apis.reference()
