@@ -222,6 +222,9 @@ int pmx_admm_init_zu(pmx_admm* h);
 int pmx_admm_step(pmx_admm* h, double step_f, int* converged, int* stalled, double* errors);
 /* fused loop of admm/sdmm iterations with constant step_f: device-side stop flag, no host round trips */
 int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, int* converged, double* errors);
+/* passes executed by the last pmx_admm_run (the halved-slack restarts of algorithms.py:503-512 reset the iteration
+ * counter, so this can exceed max_iter) and the number of restarts */
+int pmx_admm_stats(pmx_admm* h, long long* passes, int* restarts);
 
 /* ------------------------------------------------ elementwise solver primitives (generic callback path)
  * Used by the Python solvers when grad/step/prox are arbitrary user callables

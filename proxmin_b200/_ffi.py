@@ -126,6 +126,7 @@ def _declare(L):
         "pmx_admm_init_zu": [vp],
         "pmx_admm_step": [vp, C.c_double, pi, pi, pd],
         "pmx_admm_run": [vp, C.c_double, i32, pi, pi, pd],
+        "pmx_admm_stats": [vp, C.POINTER(C.c_longlong), pi],
         "pmx_pgm_update": [vp, C.POINTER(Prox), vp, vp, vp, i32, i32, f32, pd, pd],
         "pmx_axis_sum": [vp, vp, i32, i32, i32, pd],
         "pmx_matmul": [vp, vp, vp, vp, i32, i32, i32, i32],

@@ -622,6 +622,11 @@ def _init_zu(X, m=None, L=None):
     return [z for z, _ in pairs], [u for _, u in pairs]
 
 
+# passes executed / restarts of the last fused admm / sdmm solve (the halved-slack restarts of algorithms.py:503-512
+# reset the iteration counter, so a solve can execute more passes than max_iter): diagnostics for bench.py
+LAST_ADMM_STATS = {"passes": 0, "restarts": 0}
+
+
 def _admm_device(X, b, step_value, chains, e_rel, e_abs, max_iter, dual_uses_step_g):
     """Fused device loop (pmx_admm_run): the whole ADMM / SDMM iteration stays on the GPU."""
     ctx = _ffi.context()
@@ -641,6 +646,9 @@ def _admm_device(X, b, step_value, chains, e_rel, e_abs, max_iter, dual_uses_ste
         it, conv = C.c_int(0), C.c_int(0)
         err = (C.c_double * 16)()
         _ffi.check(L.pmx_admm_run(h, float(step_value), int(max_iter), C.byref(it), C.byref(conv), err))
+        passes, restarts = C.c_longlong(0), C.c_int(0)
+        _ffi.check(L.pmx_admm_stats(h, C.byref(passes), C.byref(restarts)))
+        LAST_ADMM_STATS.update(passes=int(passes.value), restarts=int(restarts.value))
         _ffi.check(L.pmx_admm_get(h, x32.ctypes.data_as(vp)))
         X[...] = x32.reshape(X.shape)
     finally:

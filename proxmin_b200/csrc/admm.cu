@@ -18,11 +18,35 @@ namespace {
 constexpr int kT = 256;
 constexpr int MAXG = 4;
 
+__device__ __forceinline__ uint64_t l2_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld4_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st4_hint(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(pol)
+               : "memory");
+}
+
 struct admm_ctl {
   int done, it, converged, reinit, restarts, max_iter;
   int changed_x, changed_r;
   float slack;
   float pad;
+  long long passes;        // passes executed since pmx_admm_run started (restarts reset `it`, not this)
   double norms[MAXG][5];   // |LX|^2, |Z|^2, |U(/step_g)|^2, |R|^2, |S|^2   (after the pass)
   double errors[MAXG][4];  // e_pri, e_dual, |R|, |S|
 };
@@ -93,46 +117,60 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
         u[i] = un;
       }
   };
-  // main part: 16-byte accesses, every load of a group issued before the arithmetic (the pass is a pure HBM
-  // stream: 7 arrays for one constraint); the buffers come from cudaMalloc, i.e. are 16-byte aligned
+  // main part: 16-byte accesses, the loads of TWO groups per thread issued before the arithmetic (the pass is a pure
+  // memory stream: 7 arrays for one constraint); the buffers come from cudaMalloc, i.e. are 16-byte aligned.
+  // L2 residency: X and U_0 are read AND rewritten by every pass -- they carry an evict_last policy on both sides, b
+  // and Z an evict_first one.  At n = 1e7 (40 MB per array, 126 MB of L2) the two kept arrays are served from L2 by
+  // the next pass: DRAM sees b + Z (12 of the 28 algorithmic bytes per element) instead of all seven streams.
+  const uint64_t pol_keep = l2_evict_last(), pol_stream = l2_evict_first();
   const size_t n4 = a.n >> 2;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
-    const float4 x4 = reinterpret_cast<const float4*>(a.X)[g];
-    const float4 b4 = reinterpret_cast<const float4*>(a.b)[g];
-    float4 z4[NG], u4[NG];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < n4; g0 += 2 * stride) {
+    float4 x4[2], b4[2], z4[2][NG], u4[2][NG];
 #pragma unroll
-    for (int i = 0; i < NG; ++i)
-      {
-        z4[i] = reinit ? x4 : reinterpret_cast<const float4*>(a.Z[i])[g];
-        u4[i] = reinit ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.U[i])[g];
-      }
-    float xo[4];
-    const float xi[4] = {x4.x, x4.y, x4.z, x4.w}, bi[4] = {b4.x, b4.y, b4.z, b4.w};
-    float zo[NG][4], uo[NG][4];
+    for (int h = 0; h < 2; ++h) {
+      const size_t g = g0 + h * stride;
+      if (g < n4) {
+        x4[h] = ld4_hint(reinterpret_cast<const float4*>(a.X) + g, pol_keep);
+        b4[h] = ld4_hint(reinterpret_cast<const float4*>(a.b) + g, pol_stream);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float z[NG], u[NG];
-#pragma unroll
-      for (int i = 0; i < NG; ++i)
-        {
-          z[i] = reinterpret_cast<const float*>(&z4[i])[c];
-          u[i] = reinterpret_cast<const float*>(&u4[i])[c];
+        for (int i = 0; i < NG; ++i) {
+          z4[h][i] = reinit ? x4[h] : ld4_hint(reinterpret_cast<const float4*>(a.Z[i]) + g, pol_stream);
+          u4[h][i] = reinit ? make_float4(0.f, 0.f, 0.f, 0.f)
+                            : ld4_hint(reinterpret_cast<const float4*>(a.U[i]) + g, i == 0 ? pol_keep : pol_stream);
         }
-      element(xi[c], bi[c], z, u, xo[c]);
+      }
+    }
 #pragma unroll
-      for (int i = 0; i < NG; ++i)
-        {
+    for (int h = 0; h < 2; ++h) {
+      const size_t g = g0 + h * stride;
+      if (g >= n4) break;
+      float xo[4];
+      const float xi[4] = {x4[h].x, x4[h].y, x4[h].z, x4[h].w}, bi[4] = {b4[h].x, b4[h].y, b4[h].z, b4[h].w};
+      float zo[NG][4], uo[NG][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float z[NG], u[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          z[i] = reinterpret_cast<const float*>(&z4[h][i])[c];
+          u[i] = reinterpret_cast<const float*>(&u4[h][i])[c];
+        }
+        element(xi[c], bi[c], z, u, xo[c]);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
           zo[i][c] = z[i];
           uo[i][c] = u[i];
         }
-    }
-    reinterpret_cast<float4*>(a.X)[g] = make_float4(xo[0], xo[1], xo[2], xo[3]);
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      {
-        reinterpret_cast<float4*>(a.Z[i])[g] = make_float4(zo[i][0], zo[i][1], zo[i][2], zo[i][3]);
-        reinterpret_cast<float4*>(a.U[i])[g] = make_float4(uo[i][0], uo[i][1], uo[i][2], uo[i][3]);
       }
+      st4_hint(reinterpret_cast<float4*>(a.X) + g, make_float4(xo[0], xo[1], xo[2], xo[3]), pol_keep);
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        st4_hint(reinterpret_cast<float4*>(a.Z[i]) + g, make_float4(zo[i][0], zo[i][1], zo[i][2], zo[i][3]), pol_stream);
+        st4_hint(reinterpret_cast<float4*>(a.U[i]) + g, make_float4(uo[i][0], uo[i][1], uo[i][2], uo[i][3]),
+                 i == 0 ? pol_keep : pol_stream);
+      }
+    }
   }
   // tail (n not a multiple of 4): scalar, the first threads of block 0
   if (blockIdx.x == 0) {
@@ -221,6 +259,7 @@ __global__ void __launch_bounds__(256) k_admm_finalize(admm_ctl* ctl, int n_g, d
     all = all && ((double)lR <= e_pri) && ((double)lS <= e_dual);                                            // utils.py:390
     for (int q = 0; q < 5; ++q) ctl->norms[i][q] = 0.0;
   }
+  ctl->passes += 1;
   const bool stalled = !ctl->changed_x && !ctl->changed_r;
   ctl->changed_x = 0;
   ctl->changed_r = 0;
@@ -462,6 +501,13 @@ int pmx_admm_run(pmx_admm* h, double step_f, int max_iter, int* iters_logged, in
     pmx_set_error("ADMM restarted more than 64 times without progress");
     return PMX_ERR_UNSUPPORTED;
   }
+  return PMX_OK;
+}
+
+int pmx_admm_stats(pmx_admm* h, long long* passes, int* restarts) {
+  PMX_REQUIRE(h != nullptr, "NULL handle");
+  if (passes) *passes = h->h_ctl->passes;
+  if (restarts) *restarts = h->h_ctl->restarts;
   return PMX_OK;
 }
 

@@ -70,6 +70,20 @@ __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long 
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
+// Gram partials are symmetric: only the 4 x 4 register tiles on or above the diagonal are computed (136 of the 256
+// tiles of a 64 x 64 Gram), by the first 136 threads -- whole warps drop out of the FMA loop -- and k_tail_final
+// mirrors them.  Thread t -> tile (ti, tj), ti <= tj, row-major over the upper triangle of an nt x nt tile grid.
+__device__ __forceinline__ bool gram_tile_of(int t, int nt, int& ti, int& tj) {
+  int row = 0, left = t;
+  while (row < nt && left >= nt - row) {
+    left -= nt - row;
+    ++row;
+  }
+  ti = row;
+  tj = row + left;
+  return row < nt;
+}
+
 // debug timeline (env PMX_TAIL_TRACE): slot 0 = earliest block start (atomicMin), other slots = latest time a phase
 // ended over all blocks (atomicMax), nanoseconds of %globaltimer
 __device__ __forceinline__ unsigned long long gtime() {
@@ -150,7 +164,9 @@ __device__ __forceinline__ void s_role(const PgmTailArgs& a, unsigned par, float
   const float* __restrict__ G = a.GS2 + (size_t)par * a.gs_stride;
   float* __restrict__ Gz = a.GS2 + (size_t)(par ^ 1u) * a.gs_stride;   // zero-filled for the next iteration
   float nd = 0.f, nn = 0.f, np = 0.f;
-  const int gi0 = (threadIdx.x >> 4) * 4, gj0 = (threadIdx.x & 15) * 4;
+  int gti, gtj;
+  const bool gram_on = gram_tile_of(threadIdx.x, (rows + 3) >> 2, gti, gtj);
+  const int gi0 = gti * 4, gj0 = gtj * 4;
   unsigned long long acc[4][2];
 #pragma unroll
   for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = 0ull;
@@ -244,6 +260,7 @@ __device__ __forceinline__ void s_role(const PgmTailArgs& a, unsigned par, float
       dd[2] = make_float4(v[4], v[4], v[5], v[5]);
       dd[3] = make_float4(v[6], v[6], v[7], v[7]);
       __syncthreads();
+      if (gram_on)
 #pragma unroll 4
       for (int cc = 0; cc < CT_COLS; ++cc) {
         const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&tileD[cc * 2 * CT_LD + 2 * gi0]);
@@ -264,6 +281,7 @@ __device__ __forceinline__ void s_role(const PgmTailArgs& a, unsigned par, float
   TSTAMP(1);
   block_accumulate3(nd, nn, np, a.acc + 4, red);
   float* out = a.gram_rep + ((size_t)NREP + (sblk % NREP)) * rows * rows;   // [1][rep][K*K]
+  if (gram_on)
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -280,9 +298,11 @@ __device__ __forceinline__ void a_role(const PgmTailArgs& a, unsigned par, float
   const int ablk = blockIdx.x;
   const int m0 = a.m_lo + ablk * a.ra;
   const int nrows = min(a.ra, a.m_hi - m0);
-  float* at = reinterpret_cast<float*>(smem);                               // [RA][K + 1] new values (Gram operand)
-  float(*red)[8] = reinterpret_cast<float(*)[8]>(at + RA * (K + 1));
-  const int ldt = K + 1;
+  const int ldt = ((K + 3) & ~3) + 4;                                       // 16-byte aligned rows
+  float* at = reinterpret_cast<float*>(smem);                               // [RA][ldt] new values (Gram operand)
+  float(*red)[8] = reinterpret_cast<float(*)[8]>(at + RA * ldt);
+  if ((K & 3) != 0)   // the columns K .. K4-1 the vector loads of the Gram touch
+    for (int i = threadIdx.x; i < RA * 4; i += TT) at[(i >> 2) * ldt + (K & ~3) + (i & 3)] = 0.f;
   const ProxChain& ch = a.chA;
   float nd = 0.f, nn = 0.f, np = 0.f;
   if (world > 1) {
@@ -413,21 +433,20 @@ __device__ __forceinline__ void a_role(const PgmTailArgs& a, unsigned par, float
     }
   }
   __syncthreads();
-  // Gram partial of these rows: A^T A, 4 x 4 outputs per thread (K <= 64: 16 x 16 threads)
+  // Gram partial of these rows: A^T A, 4 x 4 outputs per thread, upper-triangular tiles only (see gram_tile_of)
   {
-    const int gi0 = (threadIdx.x >> 4) * 4, gj0 = (threadIdx.x & 15) * 4;
-    float acc[4][4];
+    int ti, tj;
+    if (gram_tile_of(threadIdx.x, (K + 3) >> 2, ti, tj)) {
+      const int gi0 = ti * 4, gj0 = tj * 4;
+      float acc[4][4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+      for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
-    if (gi0 < K && gj0 < K) {
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
       for (int r = 0; r < nrows; ++r) {
-        float av[4], bv[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) av[p] = gi0 + p < K ? at[r * ldt + gi0 + p] : 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) bv[q] = gj0 + q < K ? at[r * ldt + gj0 + q] : 0.f;
+        const float4 a4 = *reinterpret_cast<const float4*>(&at[r * ldt + gi0]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&at[r * ldt + gj0]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -573,6 +592,12 @@ __global__ void __launch_bounds__(2 * TT) k_tail_final(const PgmTailArgs a) {
     a.acc[4 * which + grp.tid] = 0.0;
   }
   grp.sync();
+  // the roles kernel only produced the 4 x 4 tiles on or above the diagonal: mirror them
+  for (int e = grp.tid; e < kk; e += TT) {
+    const int i = e / K, j = e - i * K;
+    if ((i >> 2) > (j >> 2)) Gd[e] = Gd[j * K + i];
+  }
+  grp.sync();
   if (world > 1) {
     // all-reduce of [Gram partial | 3 norms] through inbox slots: push to slot `rank` of every rank, signal, wait, sum
     // the slots in rank order
@@ -660,7 +685,7 @@ __global__ void k_tail_seed_steps(pmx_ctl* ctl) {
 
 size_t pgm_tail_smem_bytes(int K) {
   const size_t srole = sizeof(float) * (CT_COLS * CT_LD + CT_COLS * 2 * CT_LD + CT_COLS + 24);
-  const size_t arole = sizeof(float) * ((size_t)RA * (K + 1) + 24);
+  const size_t arole = sizeof(float) * ((size_t)RA * (((K + 3) & ~3) + 4) + 24);
   return srole > arole ? srole : arole;
 }
 
