@@ -28,6 +28,11 @@ __device__ __forceinline__ uint64_t l2_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ float4 ld4_hint(const float4* p, uint64_t pol) {
   float4 v;
   asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -63,6 +68,7 @@ struct PassArgs {
   int use_slack;
   int dual_uses_step_g;
   admm_ctl* ctl;
+  int l2_mode;        // L2 residency policy of the streams (see k_admm_pass)
   float* part;        // [gridDim.x][MAXG * 5] per-block partial norms (summed by k_admm_finalize: no same-address atomics)
 };
 
@@ -122,7 +128,12 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
   // L2 residency: X and U_0 are read AND rewritten by every pass -- they carry an evict_last policy on both sides, b
   // and Z an evict_first one.  At n = 1e7 (40 MB per array, 126 MB of L2) the two kept arrays are served from L2 by
   // the next pass: DRAM sees b + Z (12 of the 28 algorithmic bytes per element) instead of all seven streams.
-  const uint64_t pol_keep = l2_evict_last(), pol_stream = l2_evict_first();
+  // (a.l2_mode, env PMX_ADMM_L2 for experiments: 0 = no distinction (evict_normal everywhere), 1 = X and U_0 kept
+  //  [default], 2 = only X kept, 3 = everything evict_first)
+  const uint64_t pol_n = l2_evict_normal();
+  const uint64_t pol_stream = a.l2_mode == 0 ? pol_n : l2_evict_first();
+  const uint64_t pol_keep = a.l2_mode == 0 ? pol_n : (a.l2_mode == 3 ? pol_stream : l2_evict_last());
+  const uint64_t pol_keep_u = a.l2_mode == 2 ? pol_stream : pol_keep;
   const size_t n4 = a.n >> 2;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < n4; g0 += 2 * stride) {
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
         for (int i = 0; i < NG; ++i) {
           z4[h][i] = reinit ? x4[h] : ld4_hint(reinterpret_cast<const float4*>(a.Z[i]) + g, pol_stream);
           u4[h][i] = reinit ? make_float4(0.f, 0.f, 0.f, 0.f)
-                            : ld4_hint(reinterpret_cast<const float4*>(a.U[i]) + g, i == 0 ? pol_keep : pol_stream);
+                            : ld4_hint(reinterpret_cast<const float4*>(a.U[i]) + g, i == 0 ? pol_keep_u : pol_stream);
         }
       }
     }
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kT) k_admm_pass(PassArgs a) {
       for (int i = 0; i < NG; ++i) {
         st4_hint(reinterpret_cast<float4*>(a.Z[i]) + g, make_float4(zo[i][0], zo[i][1], zo[i][2], zo[i][3]), pol_stream);
         st4_hint(reinterpret_cast<float4*>(a.U[i]) + g, make_float4(uo[i][0], uo[i][1], uo[i][2], uo[i][3]),
-                 i == 0 ? pol_keep : pol_stream);
+                 i == 0 ? pol_keep_u : pol_stream);
       }
     }
   }
@@ -326,6 +337,10 @@ static int admm_enqueue(pmx_admm* h, double step_base, int use_slack, int manage
   a.dual_uses_step_g = h->opts.dual_uses_step_g;
   a.ctl = h->ctl;
   a.part = h->part;
+  {
+    static const char* m = getenv("PMX_ADMM_L2");
+    a.l2_mode = m ? atoi(m) : 1;
+  }
   const bool prof = ctx->profile && ctx->prof_n < PMX_PROF_MAX;   // per-launch events around the pass (bench.py roofline)
   if (prof) PMX_CUDA(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream));
   switch (h->opts.n_g) {

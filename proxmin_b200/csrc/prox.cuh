@@ -49,7 +49,10 @@ static inline int chain_unity_axis(const ProxChain& c) {  // -1 none, 0/1 the si
 
 // Principal branch of the Lambert W function for real z >= 0 (scipy.special.lambertw of operators.py:183, whose
 // argument here is always a positive real): Halley iterations in fp64 from log1p(z) / the asymptotic series.
-__device__ inline double pmx_lambertw0(double z) {
+// NOT inlined, like pmx_maxent_elem below: the fp64 exp / log expansions are ~3000 instructions and prox_elem is
+// inlined into every unrolled chain of every fused kernel (the first version grew k_pgm_tail from 8 K to 42 K
+// instructions); the rare operator pays a function call instead.
+static __device__ __noinline__ double pmx_lambertw0(double z) {
   if (!(z > 0.0)) return z;                 // 0 -> 0, NaN -> NaN
   if (isinf(z)) return z;
   double w;
@@ -70,6 +73,26 @@ __device__ inline double pmx_lambertw0(double z) {
   return w;
 }
 
+// prox_max_entropy of one element with x > 0 (operators.py:182-183); f64 != 0: the caller's array is float64
+static __device__ __noinline__ float pmx_maxent_elem(float x, float t, int f64) {
+  if (!f64) {
+    // NumPy evaluates  gamma_ * real(lambertw(exp(X / gamma_ - 1) / gamma_))  with the fp32 array X: the argument of
+    // lambertw is an fp32 value (np.exp of an fp32 array: overflows to inf for X / gamma_ > 89), W and the product
+    // with gamma_ are fp64, the assignment rounds to fp32
+    const float a = __fsub_rn(__fdiv_rn(x, t), 1.0f);
+    const float e = (float)exp((double)a);
+    const float z = __fdiv_rn(e, t);
+    return (float)((double)t * pmx_lambertw0((double)z));
+  }
+  const double a = (double)x / (double)t - 1.0;
+  if (a < 700.0) return (float)((double)t * pmx_lambertw0(exp(a) / (double)t));
+  // exp(a) would overflow even in fp64 (the reference returns inf only beyond a = 709): solve w + log(w) = a - log(t)
+  const double Lr = a - log((double)t);
+  double w = Lr - log(Lr);
+  for (int it = 0; it < 6; ++it) w -= (w + log(w) - Lr) / (1.0 + 1.0 / w);
+  return a > 709.78 ? __int_as_float(0x7f800000) : (float)((double)t * w);
+}
+
 // One elementwise primitive.  The comparisons are written exactly like the NumPy masks of
 // the reference so that NaN, +-inf and -0.0 behave identically (support sets are bit-exact).
 __device__ __forceinline__ float prox_elem(float x, int op, float t) {
@@ -85,27 +108,9 @@ __device__ __forceinline__ float prox_elem(float x, int op, float t) {
       float s = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : ((x == 0.0f) ? 0.0f : x));  // np.sign
       return s * a;
     }
-    case PMX_OP_MAXENT: {                                             // operators.py:182-183
-      if (!(x > 0.0f)) return x;                                      // only X[X > 0] is touched
-      // NumPy evaluates  gamma_ * real(lambertw(exp(X / gamma_ - 1) / gamma_))  with the fp32 array X: the argument of
-      // lambertw is an fp32 value (np.exp of an fp32 array), W and the product with gamma_ are fp64, the assignment
-      // rounds to fp32
-      const float a = __fsub_rn(__fdiv_rn(x, t), 1.0f);
-      const float e = (float)exp((double)a);
-      const float z = __fdiv_rn(e, t);
-      return (float)((double)t * pmx_lambertw0((double)z));
-    }
-    case PMX_OP_MAXENT64: {                                           // same, caller's array is float64
-      if (!(x > 0.0f)) return x;
-      const double a = (double)x / (double)t - 1.0;
-      if (a < 700.0) return (float)((double)t * pmx_lambertw0(exp(a) / (double)t));
-      // exp(a) overflows even in fp64 (the reference returns inf there as well only beyond a = 709): solve
-      // w + log(w) = a - log(t) directly
-      const double Lr = a - log((double)t);
-      double w = Lr - log(Lr);
-      for (int it = 0; it < 6; ++it) w -= (w + log(w) - Lr) / (1.0 + 1.0 / w);
-      return a > 709.78 ? __int_as_float(0x7f800000) : (float)((double)t * w);
-    }
+    case PMX_OP_MAXENT:                                               // operators.py:182-183: only X[X > 0] is touched
+    case PMX_OP_MAXENT64:
+      return (x > 0.0f) ? pmx_maxent_elem(x, t, op == PMX_OP_MAXENT64) : x;
     default: return x;
   }
 }
