@@ -334,6 +334,95 @@ int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst
   return pmx_check_launch(ctx, "k_peer_sum");
 }
 
+// ---- small all-reduce in ONE kernel (push model): every rank writes its n values into slot `rank` of every rank's
+// inbox, signals, waits for all ranks and reduces the slots in rank order (bit-identical results everywhere).
+// Replaces the latency-bound NCCL all-reduces of a few scalars inside the adaprox / bsdmm iterations (max Psi, the
+// sub-iteration norms, the row sums of S, the constraint norms): ~6 us instead of 40-60 us at 8 ranks.
+// Inbox layout at off_bytes of the arena: [2 parity][PMX_MAX_WORLD ranks][PMX_SMALL_MAX] 8-byte slots.  The parity
+// double-buffering is safe for any sequence of exchanges on one flag set: a rank can only be one epoch ahead of the
+// slowest one (it needs everybody's signal to finish an exchange).
+// kind 1: doubles, sum.  kind 2: 32-bit words compared as signed integers, max (non-negative floats order like ints).
+namespace {
+__global__ void __launch_bounds__(256) k_small_allreduce(pmx_peer_ptrs arena, size_t off_bytes, void* buf, int n, int kind,
+                                                         unsigned* epoch, pmx_peer_ptrs flags, const unsigned* my_flags,
+                                                         int set, int world, int rank, const int* done, int* fault) {
+  if (done && *done) return;
+  __shared__ unsigned s_e;
+  __shared__ int s_fault;
+  if (threadIdx.x == 0) {
+    s_e = epoch[set] + 1;
+    epoch[set] = s_e;
+    s_fault = 0;
+  }
+  __syncthreads();
+  const unsigned e = s_e;
+  const size_t par = e & 1u;
+  for (int r = 0; r < world; ++r) {
+    double* dst = reinterpret_cast<double*>(static_cast<char*>(arena.p[r]) + off_bytes) + (par * PMX_MAX_WORLD + rank) * PMX_SMALL_MAX;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (kind == 1) dst[i] = static_cast<const double*>(buf)[i];
+      else reinterpret_cast<long long*>(dst)[i] = (long long)static_cast<const int*>(buf)[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world)
+    st_release_sys(reinterpret_cast<unsigned*>(flags.p[threadIdx.x]) + set * PMX_MAX_WORLD + rank, e);
+  if ((int)threadIdx.x < world) {
+    const unsigned* f = my_flags + set * PMX_MAX_WORLD + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(f) - e) < 0) {
+      if (clock64() - t0 > 6000000000LL) {   // ~3 s: a lost peer must not hang the GPU
+        s_fault = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_fault) {
+    if (threadIdx.x == 0 && fault) *fault = 1;
+    return;
+  }
+  const volatile double* in = reinterpret_cast<const volatile double*>(static_cast<char*>(arena.p[rank]) + off_bytes) +
+                              par * PMX_MAX_WORLD * PMX_SMALL_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (kind == 1) {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r) acc += in[(size_t)r * PMX_SMALL_MAX + i];
+      static_cast<double*>(buf)[i] = acc;
+    } else {
+      long long m = reinterpret_cast<const volatile long long*>(in)[i];
+      for (int r = 1; r < world; ++r) {
+        const long long v = reinterpret_cast<const volatile long long*>(in)[(size_t)r * PMX_SMALL_MAX + i];
+        m = v > m ? v : m;
+      }
+      static_cast<int*>(buf)[i] = (int)m;
+    }
+  }
+}
+}  // namespace
+
+size_t pmx_peer_small_bytes() { return sizeof(double) * 2 * PMX_MAX_WORLD * PMX_SMALL_MAX; }
+
+// in-place all-reduce of n <= PMX_SMALL_MAX values at `buf` (device) through the inbox at off_bytes of the arena
+int pmx_peer_small_allreduce(pmx_ctx* ctx, int set, size_t off_bytes, void* buf, int n, int kind, cudaStream_t st,
+                             const int* done, int* fault) {
+  if (n > PMX_SMALL_MAX || (kind != 1 && kind != 2)) {
+    pmx_set_error("pmx_peer_small_allreduce: n = %d, kind = %d not supported", n, kind);
+    return PMX_ERR_ARG;
+  }
+  pmx_peer_ptrs ar, fl;
+  for (int r = 0; r < PMX_MAX_WORLD; ++r) {
+    ar.p[r] = ctx->peer_arena.peer[r];
+    fl.p[r] = ctx->peer_flags.peer[r];
+  }
+  k_small_allreduce<<<1, 256, 0, st>>>(ar, off_bytes, buf, n, kind, ctx->peer_epoch, fl,
+                                       reinterpret_cast<const unsigned*>(ctx->peer_flags.local), set, ctx->world, ctx->rank,
+                                       done, fault);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_small_allreduce");
+}
+
 int pmx_peer_setup_internal(pmx_ctx* ctx) {
   ctx->peer_ok = 0;
   if (ctx->world <= 1 || ctx->world > PMX_MAX_WORLD || getenv("PMX_NO_PEER")) return PMX_OK;

@@ -54,12 +54,16 @@ struct pmx_ctl {
   int fault;         // a peer did not answer within the spin limit (multi-GPU exchange): the solve is aborted
   unsigned par_ctr;  // fused PGM tail: iterations whose factor updates are complete (parity of the gradient buffers)
   int final_pending; // fused PGM tail: the roles kernel finished an iteration that k_tail_final has not closed yet
-  int pad;
+  int paused_block;  // adaprox: block (1 = A, 2 = S) whose speculative sub-iterations did not converge; done == 2 then
+                     // freezes every following kernel until the host has finished the block (nmf_solver.cu)
+  int sub_last[2];   // adaprox: sub-iterations the last completed block update took, per block
+  int pad2[2];
 };
 
 // ---- peer-memory exchange (comm.cu): symmetric device regions mapped into every rank of the box over CUDA IPC
 #define PMX_MAX_WORLD 8
 #define PMX_PEER_SETS 4            // independent flag sets (one per exchange point of an iteration)
+#define PMX_SMALL_MAX 256          // 8-byte slots per rank of a small all-reduce inbox (comm.cu)
 struct pmx_peer_region {
   void* local;                     // this rank's allocation (cudaMalloc)
   void* peer[PMX_MAX_WORLD];       // the same region of every rank, peer[rank] == local

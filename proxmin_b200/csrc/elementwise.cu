@@ -94,6 +94,53 @@ __global__ void __launch_bounds__(kThreads) k_upd_flat(ProxChain ch, UpdIO io) {
   const size_t n = (size_t)io.rows * io.cols;
   float nd = 0.f, nn = 0.f, np = 0.f;
   const bool need_rc = io.step.mode >= 2 || io.hi != nullptr;
+  // fast path: 16-byte accesses, one 32-bit division per four elements (the scalar loop below costs a 64-bit division
+  // and three dependent 4-byte loads per element: the adaprox sub-iteration ran at 1.6 TB/s with it)
+  const bool vec = (io.cols & 3) == 0 && (n >> 2) < 0xffffffffull && !io.hi && !io.Xold_out &&
+                   ((reinterpret_cast<uintptr_t>(io.Xin) | reinterpret_cast<uintptr_t>(io.Xout) |
+                     reinterpret_cast<uintptr_t>(io.G) | reinterpret_cast<uintptr_t>(io.X0) |
+                     reinterpret_cast<uintptr_t>(io.Xprev)) & 15) == 0;
+  if (vec) {
+    const unsigned n4 = (unsigned)(n >> 2), cols4 = (unsigned)io.cols >> 2;
+    const bool prev_is_in = io.Xprev == io.Xin;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += gridDim.x * blockDim.x) {
+      unsigned r = 0, c = 0;
+      if (need_rc) {
+        r = g / cols4;
+        c = (g - r * cols4) << 2;
+      }
+      const float4 xin4 = reinterpret_cast<const float4*>(io.Xin)[g];
+      const float4 g4 = (IN != IN_PLAIN) ? reinterpret_cast<const float4*>(io.G)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 x04 = (IN == IN_ADASUB) ? reinterpret_cast<const float4*>(io.X0)[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 pv4 = prev_is_in ? xin4 : (io.Xprev ? reinterpret_cast<const float4*>(io.Xprev)[g] : make_float4(0.f, 0.f, 0.f, 0.f));
+      const float xi[4] = {xin4.x, xin4.y, xin4.z, xin4.w}, gi[4] = {g4.x, g4.y, g4.z, g4.w};
+      const float x0[4] = {x04.x, x04.y, x04.z, x04.w}, pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+      float out[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float s = step_at(io.step, (int)r, (int)c + q);
+        float ps = s, v;
+        if (IN == IN_PGM) {
+          v = __fsub_rn(xi[q], __fmul_rn(s, gi[q]));
+        } else if (IN == IN_ADASUB) {
+          const float gamma = s / io.psimax[0];
+          ps = gamma;
+          v = xi[q] - gamma / s * gi[q] * (xi[q] - x0[q]);
+        } else {
+          v = xi[q];
+        }
+        v = chain_segment(ch, 0, ch.n, v, ps);
+        out[q] = v;
+        const float d = v - pv[q];
+        nd += d * d;
+        nn += v * v;
+        np += pv[q] * pv[q];
+      }
+      reinterpret_cast<float4*>(io.Xout)[g] = make_float4(out[0], out[1], out[2], out[3]);
+    }
+    if (io.norms) block_accumulate3(nd, nn, np, io.norms);
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0, c = 0;
     if (need_rc) {
@@ -748,11 +795,18 @@ __global__ void __launch_bounds__(kThreads) k_adaprox_moments(AdaArgs a) {
     if (radam_rect) radam_r = (float)sqrt((rho - 4.0) * (rho - 2.0) * rho_inf / (rho_inf - 4.0) / (rho_inf - 2.0) / rho);
   }
   const bool need_rc = a.alpha.mode >= 2;
+  const bool small = a.n < 0xffffffffull;   // 32-bit index arithmetic (a 64-bit division per element otherwise)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
     int r = 0, c = 0;
     if (need_rc) {
-      r = (int)(i / a.cols);
-      c = (int)(i - (size_t)r * a.cols);
+      if (small) {
+        const unsigned ii = (unsigned)i, rr = ii / (unsigned)a.cols;
+        r = (int)rr;
+        c = (int)(ii - rr * (unsigned)a.cols);
+      } else {
+        r = (int)(i / a.cols);
+        c = (int)(i - (size_t)r * a.cols);
+      }
     }
     const float g = a.G[i];
     const float m = (float)((1.0 - a.b1) * (double)g + a.b1 * (double)a.M[i]);

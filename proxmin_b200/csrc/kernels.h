@@ -32,12 +32,14 @@ int launch_alpha_means(pmx_ctx* ctx, const float* X, int rows, int cols, int axi
                        const int* done);
 int launch_sub_begin(pmx_ctx* ctx, pmx_ctl* ctl, int block);
 int launch_sub_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2, int max_tau);
-int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, size_t n, pmx_ctl* ctl, int block);
+int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, size_t n, pmx_ctl* ctl, int block,
+                      unsigned short* hi = nullptr, unsigned short* lo = nullptr, int cols = 0, int ld_split = 0);
+int launch_clear_pause(pmx_ctx* ctx, pmx_ctl* ctl);
 int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, int check);
 int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const float* G, float* const* Z, float* const* U,
                        float* T, double* sums_scratch, int rows, int cols, int n_g, const ProxChain& direct,
                        const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs, bool sharded,
-                       double n_elems_global);
+                       double n_elems_global, long long xchg_off = -1);
 int launch_alpha_from_sums(pmx_ctx* ctx, const double* sums, int n, double count, float* alpha, const int* done);
 int launch_bsdmm_iter_finalize(pmx_ctx* ctx, pmx_ctl* ctl);
 

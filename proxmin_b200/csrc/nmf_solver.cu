@@ -23,6 +23,9 @@ int pmx_peer_reset(pmx_ctx* ctx);
 int pmx_peer_signal(pmx_ctx* ctx, int set, cudaStream_t st, const int* done, const double* copy_src,
                     size_t copy_offset_bytes, size_t n);
 int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done);
+size_t pmx_peer_small_bytes();
+int pmx_peer_small_allreduce(pmx_ctx* ctx, int set, size_t off_bytes, void* buf, int n, int kind, cudaStream_t st,
+                             const int* done, int* fault);
 
 struct pmx_nmf {
   pmx_ctx* ctx;
@@ -62,12 +65,18 @@ struct pmx_nmf {
   size_t off_GA, off_A, off_Ahi, off_Alo, off_inbox;   // regions of the peer arena (bytes)
   cudaGraphExec_t tail_graph;
   long long tail_graph_launches;
+  // ---- sharded adaprox / bsdmm: exchanges over peer memory (arena: [G_A pair | small all-reduce inboxes])
+  bool xchg_peer;
+  size_t xchg_ga_stride, xchg_off_small;
   bool tail_G_pending;         // the last gradients still sit in the parity buffers (tail_publish_G)
   size_t tail_G_par;
   // ---- adaprox
   pmx_adaprox_opts ada;
   float *MA, *MS, *VA, *VS, *VhA, *VhS, *Psi, *Z0, *Z1, *alphaA, *alphaS;
   int ada_it;
+  int ada_spec[2];   // sub-iterations enqueued speculatively per block (no host round trip), follows the last count
+  int ada_enq[2];    // sub-iterations enqueued for the block update in flight
+  bool ada_fuse_split; // both blocks have a prox: their commits write the bf16 operands of the next gradient kernel
   // ---- bsdmm
   pmx_bsdmm_opts bs;
   float* Zg[2][4];
@@ -132,6 +141,17 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
     if (!h->plan) PMX_CHECK(umma_plan_create(ctx, h->Y, h->ldY, h->M, h->N, h->K, &h->plan, 1));
     PMX_CHECK(umma_plan_set_W(h->plan, h->W));
     const int skip = (h->split_valid && A == h->A && S == h->S) ? 1 : 0;
+    if (h->xchg_peer && ctx->world > 1 && !defer_reduce && !ga_epoch && (want & 1) && GA) {
+      // sharded adaprox / bsdmm: the G_A partials land in the arena pair, every rank sums them out of peer memory
+      // (one-shot sum in rank order: bit-identical on every rank) instead of an NCCL all-reduce of M x K floats
+      float* ga_pair = reinterpret_cast<float*>(ctx->peer_arena.local);
+      PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, ga_pair, GS, loss, done, skip, &ctx->peer_epoch[0], h->xchg_ga_stride, want));
+      PMX_CHECK(pmx_peer_signal(ctx, 0, ctx->stream, done, nullptr, 0, 0));
+      PMX_CHECK(pmx_peer_sum(ctx, 0, 0, h->xchg_ga_stride, GA, 0, ctx->stream, done));
+      h->used_umma = true;
+      if (loss) PMX_CHECK(pmx_comm_allreduce_internal(ctx, loss, 1, 1, ctx->stream));
+      return PMX_OK;
+    }
     PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, GA, GS, loss, done, skip, ga_epoch, ga_stride, want));
     h->used_umma = true;
   } else {
@@ -158,6 +178,33 @@ static int reject_sharded_row_unity(pmx_nmf* h, const ProxChain& chS, const char
 
 static bool nmf_uses_umma(pmx_nmf* h, int kernel) {
   return kernel == 2 || (kernel == 0 && umma_supported(h->M, h->N, h->K) && (long long)h->M * h->N >= 128LL * 128);
+}
+
+// sharded adaprox / bsdmm (no fused tail): lay the peer arena out as [G_A pair | 8 small all-reduce inboxes].
+// Collective (every rank calls it from the solver's begin function); without symmetric memory NCCL stays.
+static inline size_t xchg_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static int xchg_setup(pmx_nmf* h, int kernel) {
+  pmx_ctx* ctx = h->ctx;
+  h->xchg_peer = false;
+  if (ctx->world <= 1 || !pmx_peer_available(ctx) || getenv("PMX_NO_PEER_XCHG")) return PMX_OK;
+  const size_t mk = (size_t)h->M * h->K;
+  h->xchg_ga_stride = mk;    // (pmx_peer_sum clears the other-parity buffer: the pair is 2 x mk floats)
+  h->xchg_off_small = xchg_align(2 * mk * sizeof(float));
+  pmx_peer_region* ar = nullptr;
+  if (pmx_peer_arena(ctx, h->xchg_off_small + 8 * pmx_peer_small_bytes(), &ar) != PMX_OK) return PMX_OK;
+  PMX_CHECK(pmx_peer_reset(ctx));
+  h->xchg_peer = true;
+  (void)kernel;
+  return PMX_OK;
+}
+// in-place all-reduce of a few scalars (kind 1: doubles, sum; kind 2: int32 max): peer inbox `slot` or NCCL
+static int nmf_allreduce(pmx_nmf* h, void* buf, size_t count, int kind, cudaStream_t st, int slot) {
+  pmx_ctx* ctx = h->ctx;
+  if (ctx->world <= 1) return PMX_OK;
+  if (h->xchg_peer && kind != 0 && count <= PMX_SMALL_MAX && st == ctx->stream)
+    return pmx_peer_small_allreduce(ctx, 1, h->xchg_off_small + (size_t)slot * pmx_peer_small_bytes(), buf, (int)count, kind, st,
+                                    &h->ctl->done, &h->ctl->fault);
+  return pmx_comm_allreduce_internal(ctx, buf, count, kind, st);
 }
 
 // lip/step of both blocks at (A, S): step[0] = 1/lambda_max(S S^T), step[1] = 1/lambda_max(A^T A)
@@ -677,6 +724,7 @@ int pmx_nmf_pgm_begin(pmx_nmf* h, const pmx_pgm_opts* opts) {
     if (!h->Se) PMX_CHECK(alloc_f(h->ctx, &h->Se, (size_t)h->K * h->N));
   }
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
+  h->xchg_peer = false;
   PMX_CHECK(tail_setup(h));
   // sharded run over peer memory (comm.cu): [G_A partials x 2 | (Gram(S) partial, 3 norms, pad) x 2] in the arena
   h->peer_mode = false;
@@ -938,8 +986,10 @@ int pmx_nmf_adaprox_begin(pmx_nmf* h, const pmx_adaprox_opts* opts) {
   if (!h->alphaS) PMX_CHECK(alloc_f(h->ctx, &h->alphaS, h->K));
   if (!h->bs_norms) PMX_CUDA(cudaMalloc((void**)&h->bs_norms, sizeof(double) * 256));
   h->ada_it = 0;
+  h->ada_spec[0] = h->ada_spec[1] = 3;
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
   PMX_CHECK(nmf_global_cols(h));
+  PMX_CHECK(xchg_setup(h, opts->kernel));
   return PMX_OK;
 }
 
@@ -948,11 +998,72 @@ static int launch_alpha_means_global(pmx_nmf* h) {
   pmx_ctx* ctx = h->ctx;
   double* sums = h->bs_norms + 128;
   PMX_CHECK(launch_axis_sum(ctx, h->S, h->K, h->N, 1, sums, &h->ctl->done));
-  if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, sums, (size_t)h->K, 1, ctx->stream));
+  PMX_CHECK(nmf_allreduce(h, sums, (size_t)h->K, 1, ctx->stream, 0));
   return launch_alpha_from_sums(ctx, sums, h->K, h->N_global, h->alphaS, &h->ctl->done);
 }
 
-static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
+// commit of block j (algorithms.py:398-400) with the bf16 split of the new block for the next gradient kernel
+static int adaprox_commit(pmx_nmf* h, int j) {
+  const int rows = j == 0 ? h->M : h->K, cols = j == 0 ? h->K : h->N;
+  float* X = j == 0 ? h->A : h->S;
+  unsigned short *hi = nullptr, *lo = nullptr;
+  int ld = 0;
+  if (h->plan && h->ada_fuse_split) {
+    void *Ahi, *Alo, *Shi, *Slo;
+    int ldA, ldS;
+    umma_plan_buffers(h->plan, &Ahi, &Alo, &Shi, &Slo, &ldA, &ldS);
+    hi = (unsigned short*)(j == 0 ? Ahi : Shi);
+    lo = (unsigned short*)(j == 0 ? Alo : Slo);
+    ld = j == 0 ? ldA : ldS;
+  }
+  return launch_sub_commit(h->ctx, X, h->Z0, h->Z1, (size_t)rows * cols, h->ctl, j, hi, lo, cols, ld);
+}
+
+// one proximal sub-iteration of block j (algorithms.py:387-389); `enq` = sub-iterations enqueued before this one
+static int adaprox_sub_enqueue(pmx_nmf* h, int j, int enq) {
+  pmx_ctx* ctx = h->ctx;
+  pmx_ctl* ctl = h->ctl;
+  const pmx_adaprox_opts& o = h->ada;
+  const int rows = j == 0 ? h->M : h->K, cols = j == 0 ? h->K : h->N;
+  float* X = j == 0 ? h->A : h->S;
+  StepSpec alpha;
+  memset(&alpha, 0, sizeof(alpha));
+  alpha.scale = 1.f;
+  if (o.step_mode == 0) {
+    alpha.ptr = j == 0 ? h->alphaA : h->alphaS;
+    alpha.mode = j == 0 ? 2 : 3;
+  } else {
+    alpha.mode = 0;
+    alpha.value = j == 0 ? o.alpha_A : o.alpha_S;
+  }
+  const ProxChain& ch = j == 0 ? h->chA : h->chS;
+  const float e = j == 0 ? o.e_rel_A : o.e_rel_S;
+  const float e2 = (float)((double)e * (double)e);
+  UpdIO io;
+  memset(&io, 0, sizeof(io));
+  const bool odd = enq & 1;
+  io.Xin = odd ? h->Z1 : h->Z0;
+  io.Xprev = io.Xin;
+  io.Xout = odd ? h->Z0 : h->Z1;
+  io.X0 = X;
+  io.G = h->Psi;
+  io.psimax = &ctl->psi_max[j];
+  io.norms = &ctl->norms[8];
+  io.done = &ctl->done;
+  io.done2 = &ctl->sub_done;
+  io.rows = rows; io.cols = cols;
+  io.step = alpha;
+  PMX_CHECK(launch_update(ctx, IN_ADASUB, ch, io));
+  if (j == 1)   // the sub-iteration stop test is a global norm (algorithms.py:389)
+    PMX_CHECK(nmf_allreduce(h, &ctl->norms[8], 3, 1, ctx->stream, 2));
+  return launch_sub_finalize(ctx, ctl, e2, o.prox_max_iter);
+}
+
+// Block j of an adaprox iteration (algorithms.py:375-400), enqueued WITHOUT a host round trip: moments, then `spec`
+// speculative sub-iterations (kernels that return once the stopping rule of :389 fired), then the commit -- which
+// freezes the solve (done = 2) if the rule has not fired yet; pmx_nmf_adaprox_run then finishes the block with
+// adaprox_block_resume.  spec follows the count the block needed last time.
+static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev, int spec) {
   pmx_ctx* ctx = h->ctx;
   pmx_ctl* ctl = h->ctl;
   const pmx_adaprox_opts& o = h->ada;
@@ -989,40 +1100,44 @@ static int adaprox_block(pmx_nmf* h, int j, int it, double b1, double b1_prev) {
   a.t = it + 1;
   PMX_CHECK(launch_adaprox_moments(ctx, a));
   // column-sharded S block: max(Psi) is a maximum over all ranks (algorithms.py:384)
-  if (j == 1 && ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &ctl->psi_max[1], 1, 2, ctx->stream));
+  if (j == 1) PMX_CHECK(nmf_allreduce(h, &ctl->psi_max[1], 1, 2, ctx->stream, 1));
   const bool has_prox = j == 0 ? o.has_prox_A : o.has_prox_S;
   if (!has_prox) return PMX_OK;   // algorithms.py:380
-  const ProxChain& ch = j == 0 ? h->chA : h->chS;
-  const float e = j == 0 ? o.e_rel_A : o.e_rel_S;
-  const float e2 = (float)((double)e * (double)e);
-  // proximal sub-iterations (algorithms.py:386-393): enqueue two at a time, then poll the device flag
-  int enq = 0;
+  if (spec > o.prox_max_iter) spec = o.prox_max_iter;
+  for (int enq = 0; enq < spec; ++enq) PMX_CHECK(adaprox_sub_enqueue(h, j, enq));
+  h->ada_enq[j] = spec;
+  return adaprox_commit(h, j);
+}
+
+// the solve is frozen inside block j (done == 2): continue its sub-iterations with a look at the flag every two, commit
+static int adaprox_block_resume(pmx_nmf* h, int j) {
+  pmx_ctx* ctx = h->ctx;
+  const pmx_adaprox_opts& o = h->ada;
+  const int rows = j == 0 ? h->M : h->K, cols = j == 0 ? h->K : h->N;
+  float* X = j == 0 ? h->A : h->S;
+  PMX_CHECK(launch_clear_pause(ctx, h->ctl));
+  int enq = h->ada_enq[j];
   while (enq < o.prox_max_iter) {
-    for (int rep = 0; rep < 2 && enq < o.prox_max_iter; ++rep, ++enq) {
-      UpdIO io;
-      memset(&io, 0, sizeof(io));
-      const bool odd = enq & 1;
-      io.Xin = odd ? h->Z1 : h->Z0;
-      io.Xprev = io.Xin;
-      io.Xout = odd ? h->Z0 : h->Z1;
-      io.X0 = X;
-      io.G = h->Psi;
-      io.psimax = &ctl->psi_max[j];
-      io.norms = &ctl->norms[8];
-      io.done = &ctl->done;
-      io.done2 = &ctl->sub_done;
-      io.rows = rows; io.cols = cols;
-      io.step = alpha;
-      PMX_CHECK(launch_update(ctx, IN_ADASUB, ch, io));
-      if (j == 1 && ctx->world > 1)   // the sub-iteration stop test is a global norm (algorithms.py:389)
-        PMX_CHECK(pmx_comm_allreduce_internal(ctx, &ctl->norms[8], 3, 1, ctx->stream));
-      PMX_CHECK(launch_sub_finalize(ctx, ctl, e2, o.prox_max_iter));
-    }
+    for (int rep = 0; rep < 2 && enq < o.prox_max_iter; ++rep, ++enq) PMX_CHECK(adaprox_sub_enqueue(h, j, enq));
     PMX_CHECK(pull_ctl(h));
     if (h->h_ctl->sub_done || h->h_ctl->done) break;
   }
-  PMX_CHECK(launch_sub_commit(ctx, X, h->Z0, h->Z1, n, ctl, j));
-  return PMX_OK;
+  (void)rows; (void)cols; (void)X; (void)ctx;
+  return adaprox_commit(h, j);
+}
+
+// rest of an iteration after block j_done (exclusive): the remaining block, the convergence norms, the finalize step
+static int adaprox_iteration_tail(pmx_nmf* h, int from_block, int it, double b1, double b1_prev) {
+  pmx_ctx* ctx = h->ctx;
+  const pmx_adaprox_opts& o = h->ada;
+  for (int j = from_block; j < 2; ++j) PMX_CHECK(adaprox_block(h, j, it, b1, b1_prev, h->ada_spec[j]));
+  if (o.check_convergence) {   // algorithms.py:403-410
+    PMX_CHECK(launch_diff_norms(ctx, h->A, h->A_old, (size_t)h->M * h->K, &h->ctl->norms[0], &h->ctl->done));
+    PMX_CHECK(launch_diff_norms(ctx, h->S, h->S_old, (size_t)h->K * h->N, &h->ctl->norms[3], &h->ctl->done));
+    PMX_CHECK(nmf_allreduce(h, &h->ctl->norms[3], 3, 1, ctx->stream, 3));
+  }
+  const float eA = o.e_rel_A, eS = o.e_rel_S;
+  return launch_adaprox_finalize(ctx, h->ctl, (float)((double)eA * eA), (float)((double)eS * eS), o.check_convergence);
 }
 
 int pmx_nmf_adaprox_run(pmx_nmf* h, int n_iter, const double* b1, const double* b1_prev, int* iters_done, int* conv_A,
@@ -1032,32 +1147,55 @@ int pmx_nmf_adaprox_run(pmx_nmf* h, int n_iter, const double* b1, const double* 
   const pmx_adaprox_opts& o = h->ada;
   PMX_CHECK(pull_ctl(h));
   const int it0 = h->h_ctl->it;
-  for (int i = 0; i < n_iter; ++i) {
-    if (h->h_ctl->done) break;
-    const int it = h->ada_it;
+  const int ada_it0 = h->ada_it;
+  // No host round trip inside an iteration: the control block is read every `poll` iterations.  A block whose
+  // speculative sub-iterations did not suffice freezes the device side (done = 2, see k_sub_commit); the host then
+  // finishes that block, re-enqueues the rest of its iteration and continues behind it (the frozen kernels of the
+  // iterations that were already enqueued did nothing).
+  const int poll = 4;
+  h->ada_fuse_split = o.has_prox_A && o.has_prox_S && nmf_uses_umma(h, o.kernel);
+  int i = 0;
+  while (i < n_iter) {
+    const int it = ada_it0 + i;
     PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, nullptr, o.kernel, &h->ctl->done));   // algorithms.py:369
     if (o.step_mode == 0) {                                                                     // algorithms.py:370
       PMX_CHECK(launch_alpha_means(ctx, h->A, h->M, h->K, 0, h->bs_norms, h->alphaA, &h->ctl->done));
       PMX_CHECK(launch_alpha_means_global(h));
     }
-    PMX_CHECK(adaprox_block(h, 0, it, b1[i], b1_prev[i]));
-    PMX_CHECK(adaprox_block(h, 1, it, b1[i], b1_prev[i]));
-    if (o.check_convergence) {   // algorithms.py:403-410
-      PMX_CHECK(launch_diff_norms(ctx, h->A, h->A_old, (size_t)h->M * h->K, &h->ctl->norms[0], &h->ctl->done));
-      PMX_CHECK(launch_diff_norms(ctx, h->S, h->S_old, (size_t)h->K * h->N, &h->ctl->norms[3], &h->ctl->done));
-      if (ctx->world > 1) PMX_CHECK(pmx_comm_allreduce_internal(ctx, &h->ctl->norms[3], 3, 1, ctx->stream));
+    PMX_CHECK(adaprox_iteration_tail(h, 0, it, b1[i], b1_prev[i]));
+    h->split_valid = h->ada_fuse_split && h->used_umma && h->plan != nullptr;   // the commits wrote the bf16 operands
+    ++i;
+    if (i % poll != 0 && i < n_iter) continue;
+    PMX_CHECK(pull_ctl(h));
+    while (h->h_ctl->done == 2) {
+      const int k = h->h_ctl->it - it0;          // iteration (index inside this call) the device froze in
+      const int j = h->h_ctl->paused_block - 1;
+      if (k < 0 || k >= n_iter || j < 0 || j > 1) {
+        pmx_set_error("adaprox: inconsistent pause state (iteration %d, block %d)", k, j);
+        return PMX_ERR_CUDA;
+      }
+      PMX_CHECK(adaprox_block_resume(h, j));
+      PMX_CHECK(adaprox_iteration_tail(h, j + 1, ada_it0 + k, b1[k], b1_prev[k]));
+      PMX_CHECK(pull_ctl(h));
+      if (h->h_ctl->done != 2) i = k + 1;        // continue behind the repaired iteration
     }
-    const float eA = o.e_rel_A, eS = o.e_rel_S;
-    PMX_CHECK(launch_adaprox_finalize(ctx, h->ctl, (float)((double)eA * eA), (float)((double)eS * eS), o.check_convergence));
-    h->ada_it += 1;
-    PMX_CHECK(pull_ctl(h));   // the sub-iteration loop syncs anyway; keeps `done` current
+    for (int j = 0; j < 2; ++j) {                // next time: what the block needed last time, plus a margin
+      const int want = h->h_ctl->sub_last[j] + 1;
+      h->ada_spec[j] = want < 2 ? 2 : (want > 64 ? 64 : want);
+    }
+    if (h->h_ctl->done) break;
   }
+  h->ada_it = ada_it0 + (h->h_ctl->it - it0);
   PMX_CHECK(pull_ctl(h));
   if (iters_done) *iters_done = h->h_ctl->it - it0;
   if (conv_A) *conv_A = h->h_ctl->conv[0];
   if (conv_S) *conv_S = h->h_ctl->conv[1];
   if (sub_A) *sub_A = h->h_ctl->sub_total[0];
   if (sub_S) *sub_S = h->h_ctl->sub_total[1];
+  if (h->h_ctl->fault) {
+    pmx_set_error("multi-GPU exchange timed out: a peer did not reach iteration %d", h->h_ctl->it);
+    return PMX_ERR_NCCL;
+  }
   return PMX_OK;
 }
 
@@ -1098,6 +1236,7 @@ int pmx_nmf_bsdmm_begin(pmx_nmf* h, const pmx_bsdmm_opts* opts) {
   PMX_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(pmx_ctl), h->ctx->stream));
   h->bs_it = 0;
   PMX_CHECK(nmf_global_cols(h));
+  PMX_CHECK(xchg_setup(h, opts->kernel));
   return PMX_OK;
 }
 
@@ -1130,7 +1269,8 @@ int pmx_nmf_bsdmm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int*
     PMX_CHECK(nmf_steps_join(h));
     PMX_CHECK(launch_bsdmm_block(ctx, h->ctl, 1, h->S, h->GS, h->Zg[1], h->Ug[1], h->Z0, sums, h->K, h->N, o.n_g_S, dS,
                                  gS, &h->ctl->step[1], h->bs_norms + 32, o.e_rel_S, o.e_abs_S, true,
-                                 (double)h->K * h->N_global));
+                                 (double)h->K * h->N_global,
+                                 h->xchg_peer ? (long long)(h->xchg_off_small + 4 * pmx_peer_small_bytes()) : -1));
     PMX_CHECK(launch_bsdmm_iter_finalize(ctx, h->ctl));
     if ((i + 1) % 8 == 0) PMX_CHECK(pull_ctl(h));
   }

@@ -1,8 +1,12 @@
 // Small elementwise / reduction kernels used by the adaprox and bsdmm device loops
 // (algorithms.py:365-410, :800-844; utils.py:295-391).  All are single coalesced passes.
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 int pmx_comm_allreduce_internal(pmx_ctx* ctx, void* buf, size_t count, int kind, cudaStream_t st);
+int pmx_peer_small_allreduce(pmx_ctx* ctx, int set, size_t off_bytes, void* buf, int n, int kind, cudaStream_t st,
+                             const int* done, int* fault);
 
 namespace {
 
@@ -114,12 +118,47 @@ __global__ void k_sub_finalize(pmx_ctl* ctl, float e2, int max_tau) {
   if (conv || ctl->sub_tau >= max_tau) ctl->sub_done = 1;
 }
 // X <- z (the buffer selected by the parity), Sub_iter[j] += tau   (algorithms.py:398-400)
+// hi / lo (optional): bf16 split of the committed block, element (r, c) at [r * ld_split + c] -- the operands of the
+// next gradient kernel (saves the two separate split passes of an adaprox iteration)
 __global__ void __launch_bounds__(kT) k_sub_commit(float* __restrict__ X, const float* __restrict__ Z0,
-                                                   const float* __restrict__ Z1, size_t n, pmx_ctl* ctl, int block) {
+                                                   const float* __restrict__ Z1, size_t n, pmx_ctl* ctl, int block,
+                                                   unsigned short* __restrict__ hi, unsigned short* __restrict__ lo,
+                                                   int cols, int ld_split) {
   if (ctl->done) return;
+  if (!ctl->sub_done) {
+    // the sub-iterations enqueued speculatively (no host round trip) did not reach the stopping rule: freeze the solve
+    // (done = 2: every following kernel returns) until the host has finished this block the slow way
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ctl->paused_block = block + 1;
+      __threadfence();
+      ctl->done = 2;
+    }
+    return;
+  }
   const float* src = ctl->sub_parity ? Z1 : Z0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) X[i] = src[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->sub_total[block] += ctl->sub_tau;
+  if (hi && n < 0xffffffffull) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)n; i += gridDim.x * blockDim.x) {
+      const float v = src[i];
+      X[i] = v;
+      const unsigned r = i / (unsigned)cols, c = i - r * (unsigned)cols;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      hi[(size_t)r * ld_split + c] = __bfloat16_as_ushort(h);
+      lo[(size_t)r * ld_split + c] = __bfloat16_as_ushort(l);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) X[i] = src[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->sub_total[block] += ctl->sub_tau;
+    ctl->sub_last[block] = ctl->sub_tau;
+  }
+}
+__global__ void k_clear_pause(pmx_ctl* ctl) {
+  if (ctl->done == 2) {
+    ctl->done = 0;
+    ctl->paused_block = 0;
+  }
 }
 // sub-iteration with ping-pong buffers needs the buffer roles resolved on the device
 __global__ void k_adaprox_finalize(pmx_ctl* ctl, float e2A, float e2S, int check) {
@@ -341,10 +380,17 @@ int launch_sub_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2, int max_tau) {
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_sub_finalize");
 }
-int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, size_t n, pmx_ctl* ctl, int block) {
-  k_sub_commit<<<grid_for(ctx, n), kT, 0, ctx->stream>>>(X, Z0, Z1, n, ctl, block);
+int launch_sub_commit(pmx_ctx* ctx, float* X, const float* Z0, const float* Z1, size_t n, pmx_ctl* ctl, int block,
+                      unsigned short* hi, unsigned short* lo, int cols, int ld_split) {
+  if (n >= 0xffffffffull) hi = lo = nullptr;
+  k_sub_commit<<<grid_for(ctx, n), kT, 0, ctx->stream>>>(X, Z0, Z1, n, ctl, block, hi, lo, cols, ld_split);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_sub_commit");
+}
+int launch_clear_pause(pmx_ctx* ctx, pmx_ctl* ctl) {
+  k_clear_pause<<<1, 1, 0, ctx->stream>>>(ctl);
+  PMX_LAUNCHED(ctx);
+  return pmx_check_launch(ctx, "k_clear_pause");
 }
 int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, int check) {
   k_adaprox_finalize<<<1, 1, 0, ctx->stream>>>(ctl, e2A, e2S, check);
@@ -356,7 +402,7 @@ int launch_adaprox_finalize(pmx_ctx* ctx, pmx_ctl* ctl, float e2A, float e2S, in
 int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const float* G, float* const* Z, float* const* U,
                        float* T, double* sums_scratch, int rows, int cols, int n_g, const ProxChain& direct,
                        const ProxChain* g, const float* step_f, double* norms, float e_rel, float e_abs, bool sharded,
-                       double n_elems_global) {
+                       double n_elems_global, long long xchg_off) {
   BsArgs a;
   memset(&a, 0, sizeof(a));
   a.X = X; a.G = G; a.T = T;
@@ -384,8 +430,13 @@ int launch_bsdmm_block(pmx_ctx* ctx, pmx_ctl* ctl, int block, float* X, const fl
     k_bsdmm_zu<<<grid, kT, 0, ctx->stream>>>(a, i, fused ? 1 : 0);
     PMX_LAUNCHED(ctx);
   }
-  if (sharded && ctx->world > 1)   // the S block is column-sharded: its norms are sums over the ranks
-    PMX_CHECK(pmx_comm_allreduce_internal(ctx, norms, (size_t)(n_g > 0 ? n_g * 5 : 5), 1, ctx->stream));
+  if (sharded && ctx->world > 1) {   // the S block is column-sharded: its norms are sums over the ranks
+    const int cnt = n_g > 0 ? n_g * 5 : 5;
+    if (xchg_off >= 0)   // inbox in the peer arena (comm.cu): one small kernel instead of an NCCL all-reduce
+      PMX_CHECK(pmx_peer_small_allreduce(ctx, 1, (size_t)xchg_off, norms, cnt, 1, ctx->stream, &ctl->done, &ctl->fault));
+    else
+      PMX_CHECK(pmx_comm_allreduce_internal(ctx, norms, (size_t)cnt, 1, ctx->stream));
+  }
   k_bsdmm_block_finalize<<<1, 1, 0, ctx->stream>>>(ctl, norms, n_g, n_elems_global, e_rel, e_abs, block);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "bsdmm block");
