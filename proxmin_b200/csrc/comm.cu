@@ -143,12 +143,17 @@ __global__ void k_peer_signal(unsigned* epoch, pmx_peer_ptrs flags, int set, int
 // dst[i] = sum_r part_r[parity][i] (rank order), local other-parity buffer cleared; T = float or double
 template <typename T>
 __global__ void k_peer_sum(pmx_peer_ptrs parts, size_t offset_bytes, size_t n, T* dst, const unsigned* epoch,
-                           const unsigned* my_flags, int set, int world, int rank, const int* done) {
+                           const unsigned* my_flags, int set, int world, int rank, const int* done, int* fault) {
   if (done && *done) return;
   const unsigned e = epoch[set];
   if ((int)threadIdx.x < world) {
     const unsigned* f = my_flags + set * PMX_MAX_WORLD + threadIdx.x;
+    const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - e) < 0) {
+      if (clock64() - t0 > 6000000000LL) {   // ~3 s of SM clocks: a lost peer must not hang the GPU
+        if (fault) *fault = 1;
+        break;
+      }
     }
   }
   __syncthreads();
@@ -318,7 +323,8 @@ int pmx_peer_reset(pmx_ctx* ctx) {
 }
 
 // dst = sum over ranks of the partials; kind 0 fp32, 1 fp64
-int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done) {
+int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done,
+                 int* fault) {
   pmx_peer_ptrs parts;
   for (int r = 0; r < PMX_MAX_WORLD; ++r) parts.p[r] = ctx->peer_arena.peer[r];
   const unsigned* my_flags = reinterpret_cast<const unsigned*>(ctx->peer_flags.local);
@@ -327,9 +333,9 @@ int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst
   if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
   if (blocks < 1) blocks = 1;
   if (kind == 0)
-    k_peer_sum<float><<<blocks, 256, 0, st>>>(parts, offset_bytes, n, (float*)dst, ctx->peer_epoch, my_flags, set, ctx->world, ctx->rank, done);
+    k_peer_sum<float><<<blocks, 256, 0, st>>>(parts, offset_bytes, n, (float*)dst, ctx->peer_epoch, my_flags, set, ctx->world, ctx->rank, done, fault);
   else
-    k_peer_sum<double><<<blocks, 256, 0, st>>>(parts, offset_bytes, n, (double*)dst, ctx->peer_epoch, my_flags, set, ctx->world, ctx->rank, done);
+    k_peer_sum<double><<<blocks, 256, 0, st>>>(parts, offset_bytes, n, (double*)dst, ctx->peer_epoch, my_flags, set, ctx->world, ctx->rank, done, fault);
   PMX_LAUNCHED(ctx);
   return pmx_check_launch(ctx, "k_peer_sum");
 }

@@ -22,7 +22,8 @@ int pmx_peer_arena(pmx_ctx* ctx, size_t bytes, pmx_peer_region** out);
 int pmx_peer_reset(pmx_ctx* ctx);
 int pmx_peer_signal(pmx_ctx* ctx, int set, cudaStream_t st, const int* done, const double* copy_src,
                     size_t copy_offset_bytes, size_t n);
-int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done);
+int pmx_peer_sum(pmx_ctx* ctx, int set, size_t offset_bytes, size_t n, void* dst, int kind, cudaStream_t st, const int* done,
+                 int* fault = nullptr);
 size_t pmx_peer_small_bytes();
 int pmx_peer_small_allreduce(pmx_ctx* ctx, int set, size_t off_bytes, void* buf, int n, int kind, cudaStream_t st,
                              const int* done, int* fault);
@@ -147,7 +148,7 @@ int nmf_gradient(pmx_nmf* h, const float* A, const float* S, float* GA, float* G
       float* ga_pair = reinterpret_cast<float*>(ctx->peer_arena.local);
       PMX_CHECK(launch_grad_umma(ctx, h->plan, A, S, ga_pair, GS, loss, done, skip, &ctx->peer_epoch[0], h->xchg_ga_stride, want));
       PMX_CHECK(pmx_peer_signal(ctx, 0, ctx->stream, done, nullptr, 0, 0));
-      PMX_CHECK(pmx_peer_sum(ctx, 0, 0, h->xchg_ga_stride, GA, 0, ctx->stream, done));
+      PMX_CHECK(pmx_peer_sum(ctx, 0, 0, h->xchg_ga_stride, GA, 0, ctx->stream, done, &h->ctl->fault));
       h->used_umma = true;
       if (loss) PMX_CHECK(pmx_comm_allreduce_internal(ctx, loss, 1, 1, ctx->stream));
       return PMX_OK;
@@ -796,7 +797,7 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
   {  // the two block updates are independent (Jacobi, algorithms.py:105-108): A on the side stream, S on the main one
     PMX_CUDA(cudaEventRecord(ctx->ev_fork2, ctx->stream));
     PMX_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
-    if (peer) PMX_CHECK(pmx_peer_sum(ctx, 0, 0, mk, h->GA, 0, ctx->aux, done));
+    if (peer) PMX_CHECK(pmx_peer_sum(ctx, 0, 0, mk, h->GA, 0, ctx->aux, done, &h->ctl->fault));
     else if (ga_on_aux) PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->GA, mk, 0, ctx->aux));
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->aux;
@@ -834,7 +835,7 @@ static int pgm_enqueue_iteration(pmx_nmf* h) {
       normsS = h->gramS + kk;
       if (peer) {
         PMX_CHECK(pmx_peer_signal(ctx, 1, ctx->stream, done, h->gramS, h->peer_off_gram, kk + 4));
-        PMX_CHECK(pmx_peer_sum(ctx, 1, h->peer_off_gram, kk + 4, h->gramS, 1, ctx->stream, done));
+        PMX_CHECK(pmx_peer_sum(ctx, 1, h->peer_off_gram, kk + 4, h->gramS, 1, ctx->stream, done, &h->ctl->fault));
       } else {
         PMX_CHECK(pmx_comm_allreduce_internal(ctx, h->gramS, kk + 3, 1, ctx->stream));
       }
@@ -1278,6 +1279,10 @@ int pmx_nmf_bsdmm_run(pmx_nmf* h, int n_iter, int* iters_done, int* conv_A, int*
   if (iters_done) *iters_done = h->h_ctl->it - it0;
   if (conv_A) *conv_A = h->h_ctl->conv[0];
   if (conv_S) *conv_S = h->h_ctl->conv[1];
+  if (h->h_ctl->fault) {
+    pmx_set_error("multi-GPU exchange timed out: a peer did not reach iteration %d", h->h_ctl->it);
+    return PMX_ERR_NCCL;
+  }
   if (h->h_ctl->nonfinite) {
     pmx_set_error("Gram matrix contains infs or NaNs (iteration %d)", h->h_ctl->it);
     return PMX_ERR_NONFINITE;

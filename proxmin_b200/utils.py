@@ -318,6 +318,73 @@ def initZU(X, L):
     return Z, U
 
 
+def do_the_mm(X, step_f, Z, U, prox_g, step_g, L):
+    """utils.py:295-304 on the device (Z, U updated in place); returns (LX, R, S).  ``L``: a MatrixAdapter."""
+    from . import algorithms as _alg
+
+    LX, R, S, _ = _alg._mm(X, Z, U, prox_g, _alg._device_chain(prox_g), step_g, True, L=_alg._linop(L))
+    return LX, R, S
+
+
+def update_variables(X, Z, U, prox_f, step_f, prox_g, step_g, L):
+    """utils.py:307-346: one ADMM / SDMM variable update (X, Z, U in place); returns (LX, R, S)."""
+    from . import algorithms as _alg
+
+    if hasattr(prox_g, "__iter__"):
+        chains = [_alg._device_chain(pg) for pg in prox_g]
+        Ls = [_alg._linop(l) for l in L] if isinstance(L, list) else _alg._linop(L)
+    else:
+        chains = _alg._device_chain(prox_g) if prox_g is not None else None
+        Ls = _alg._linop(L)
+    LX, R, S, _ = _alg._update_variables(X, Z, U, prox_f, step_f, prox_g, chains, step_g, True, L=Ls)
+    return LX, R, S
+
+
+def get_variable_errors(X, L, LX, Z, U, step_g, e_rel, e_abs=0):
+    """utils.py:349-363: tolerances (e_pri, e_dual) of one constraint, norms on the device."""
+    from . import _dev
+    from . import algorithms as _alg
+
+    Lad = _alg._linop(L)
+    spec = _alg._spec(Lad)
+    e_pri2 = np.sqrt(Z.size) * e_abs / spec + e_rel * np.max([np.sqrt(np.float32(_dev.sumsq(LX))),
+                                                             np.sqrt(np.float32(_dev.sumsq(Z)))])
+    LTU = U if Lad is None else Lad.T.dot(U)
+    lU = np.sqrt(np.float32(_dev.sumsq(LTU)))
+    if step_g is not None:
+        lU = lU / np.float32(step_g)
+    e_dual2 = np.sqrt(X.size) * e_abs / spec + e_rel * lU
+    return e_pri2, e_dual2
+
+
+def check_constraint_convergence(X, L, LX, Z, U, R, S, step_f, step_g, e_rel, e_abs):
+    """utils.py:366-391: Boyd (2011) section 3.3.1 stopping rule, recursive over lists of constraints."""
+    from . import _dev
+
+    if isinstance(L, list):
+        convergence, errors = True, []
+        for i in range(len(L)):
+            c, e = check_constraint_convergence(X, L[i], LX[i], Z[i], U[i], R[i], S[i], step_f, step_g[i], e_rel, e_abs)
+            convergence &= c
+            errors.append(e)
+        return convergence, errors
+    e_pri, e_dual = get_variable_errors(X, L, LX, Z, U, step_g, e_rel, e_abs)
+    lR = np.sqrt(np.float32(_dev.sumsq(R)))
+    lS = np.sqrt(np.float32(_dev.sumsq(S)))
+    return (lR <= e_pri) and (lS <= e_dual), (e_pri, e_dual, lR, lS)
+
+
+def check_convergence(newX, oldX, e_rel):
+    """utils.py:394-406 (Langville 2014, section 5): sum(new * old) >= (1 - e_rel^2) sum(old^2), sums on the device."""
+    from . import _dev
+
+    dot, _ = _dev.dot_diff(newX, np.zeros_like(newX), oldX)      # sum((new - 0) * old)
+    norms = [newX.dtype.type(dot) if newX.dtype.kind == "f" else dot, oldX.dtype.type(_dev.sumsq(oldX))
+             if oldX.dtype.kind == "f" else _dev.sumsq(oldX)]
+    convergent = norms[0] >= (1 - e_rel ** 2) * norms[1]
+    return convergent, norms
+
+
 class ConstantStep(object):
     """``step_f(X, it=None) -> value``.  A plain callable for any solver; the device ADMM loop recognises
     it and keeps the whole iteration on the GPU (an arbitrary Python step function forces one host

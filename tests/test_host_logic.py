@@ -116,3 +116,16 @@ def test_public_names_and_signatures_equal_the_reference():
     for n in ("Traceback", "NullCallback", "NesterovAccelerator", "get_spectral_norm", "l2sq", "l2", "_as_tuple",
               "_copy_tuple"):
         assert hasattr(pmx.utils, n), n
+    # every public name of the reference's utils / operators modules exists with the same parameters
+    for modname in ("utils", "operators"):
+        rmod, pmod = getattr(ref, modname), getattr(pmx, modname)
+        for n in dir(rmod):
+            obj = getattr(rmod, n)
+            if n.startswith("_") or getattr(obj, "__module__", None) != rmod.__name__:
+                continue
+            assert hasattr(pmod, n), "%s.%s is missing" % (modname, n)
+            if inspect.isfunction(obj):
+                assert list(inspect.signature(getattr(pmod, n)).parameters) == list(inspect.signature(obj).parameters), n
+            elif inspect.isclass(obj) and "__init__" in vars(obj):
+                assert list(inspect.signature(getattr(pmod, n).__init__).parameters)[:len(inspect.signature(obj.__init__).parameters)] \
+                    == list(inspect.signature(obj.__init__).parameters), n
