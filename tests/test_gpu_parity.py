@@ -412,6 +412,54 @@ def test_matrix_adapter(product):
     assert ident.dot(x) is x and ident.T is ident and ident.spectral_norm == 1
 
 
+def test_utils_admm_primitives(product):
+    """utils.update_variables / do_the_mm / get_variable_errors / check_constraint_convergence / check_convergence
+    (utils.py:295-406) as public functions: one ADMM step with a dense L against the same NumPy expressions."""
+    from functools import partial
+
+    import proxmin_b200 as pmx
+
+    rng = np.random.default_rng(9)
+    L = (rng.standard_normal((10, 16)) / 4).astype(np.float32)
+    b = rng.standard_normal(16).astype(np.float32)
+    X0 = rng.standard_normal(16).astype(np.float32)
+    prox_f = lambda X, s: X - s * (X - b)          # noqa: E731
+    prox_g = partial(pmx.prox_soft, thresh=0.1)
+    sf, sg = np.float32(0.5), np.float32(0.7)
+    # reference expressions (utils.py:295-346) in NumPy
+    Xr = X0.copy()
+    Zr = L.dot(Xr).copy()
+    Ur = np.zeros_like(Zr)
+    Ur += 0.05
+    dX = sf / sg * L.T.dot(L.dot(Xr) - Zr + Ur)
+    Xr[:] = prox_f(Xr - dX, sf)
+    LXr = L.dot(Xr)
+    t = LXr + Ur
+    Zn = np.sign(t) * np.maximum(np.abs(t) - 0.1 * sg, 0)
+    Rr = LXr - Zn
+    Sr = -1 / sg * L.T.dot(Zn - Zr)
+    Ur2 = Ur + Rr
+    # product
+    Xp = X0.copy()
+    ad = pmx.utils.MatrixAdapter(L)
+    Zp, Up = pmx.utils.initZU(Xp, ad)
+    Up += 0.05
+    LXp, Rp, Sp = pmx.utils.update_variables(Xp, Zp, Up, prox_f, sf, prox_g, sg, ad)
+    for got, want, name in ((Xp, Xr, "X"), (LXp, LXr, "LX"), (Zp, Zn, "Z"), (Up, Ur2, "U"), (Rp, Rr, "R"), (Sp, Sr, "S")):
+        assert np.allclose(got, want, rtol=2e-5, atol=2e-6), name
+    conv, (e_pri, e_dual, lR, lS) = pmx.utils.check_constraint_convergence(Xp, ad, LXp, Zp, Up, Rp, Sp, sf, sg, 1e-3, 0.01)
+    spec = np.linalg.eigvalsh(L.T.astype(np.float64) @ L.astype(np.float64)).max()
+    l2 = lambda x: np.sqrt((x.astype(np.float64) ** 2).sum())   # noqa: E731
+    assert np.isclose(e_pri, np.sqrt(Zn.size) * 0.01 / spec + 1e-3 * max(l2(LXr), l2(Zn)), rtol=1e-4)
+    assert np.isclose(e_dual, np.sqrt(Xr.size) * 0.01 / spec + 1e-3 * l2(L.T.dot(Ur2) / sg), rtol=1e-4)
+    assert np.isclose(lR, l2(Rr), rtol=1e-4) and np.isclose(lS, l2(Sr), rtol=1e-4)
+    assert conv == bool(l2(Rr) <= e_pri and l2(Sr) <= e_dual)
+    new, old = rng.random((4, 9)).astype(np.float32), rng.random((4, 9)).astype(np.float32)
+    c, norms = pmx.utils.check_convergence(new, old, 0.5)
+    assert np.allclose(norms, [np.sum(new * old), np.sum(old ** 2)], rtol=1e-5)
+    assert c == bool(np.sum(new * old) >= (1 - 0.25) * np.sum(old ** 2))
+
+
 def test_nmf_weighted_likelihood(product):
     """Weighted likelihood W (nmf.py:25, 40): gradient / loss, fused adaprox loop, PGM with a user step (callback
     loop, Y and W resident on the device)"""

@@ -7,7 +7,9 @@ replays that exchange sequence with gloo collectives around the oracle's
 NumPy pieces and checks it against the unsharded oracle: it pins the partition (workloads.shard_columns)
 and the list of reduced quantities that the device path relies on.  Two spellings of the exchange: an all-reduce
 (the NCCL fallback) and an all-gather followed by a sum in rank order in the working precision -- what the
-peer-memory kernels of comm.cu do -- for which the replicas of A must stay bit-identical on every rank."""
+peer-memory kernels of comm.cu do -- for which the replicas of A must stay bit-identical on every rank -- and the
+reduce-scatter / all-gather of the fused PGM tail of round 2 (mode "scatter": every rank sums and updates only its row slice
+of A, the new rows are gathered, the Gram partials of both new factors are exchanged for the next steps)."""
 import os
 import sys
 
@@ -49,6 +51,53 @@ def _worker(rank, world, port, out, mode="allreduce"):
     Yl, Sl = Y[:, lo:hi].copy(), S[:, lo:hi].copy()
     A = A.copy()
     iters = 25
+    if mode == "scatter":
+        # The fused PGM tail of round 2 (pgm_tail.cu): reduce-scatter of the G_A partials by row slice, the A update on
+        # the slice only, all-gather of the new rows; the Gram partials of BOTH new factors (rows of A per rank, columns
+        # of S per rank) summed in rank order give the steps of the next iteration.
+        def gather_sum(x):
+            x = np.ascontiguousarray(x)
+            parts = [torch.empty_like(torch.from_numpy(x)) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(x))
+            acc = np.zeros_like(x)
+            for p in parts:
+                acc = acc + p.numpy()
+            return acc, parts
+
+        m_lo, m_hi = M * rank // world, M * (rank + 1) // world
+        slices = [(M * r // world, M * (r + 1) // world) for r in range(world)]
+        gramS, _ = gather_sum(Sl.astype(np.float64).dot(Sl.T))
+        gramA, _ = gather_sum(A[m_lo:m_hi].astype(np.float64).T.dot(A[m_lo:m_hi]))
+        for it in range(iters):
+            R = A.dot(Sl) - Yl
+            GA_part = np.ascontiguousarray(R.dot(Sl.T))
+            GS = A.T.dot(R)
+            step_A = np.float32(1 / np.linalg.eigvalsh(gramS).max())
+            step_S = np.float32(1 / np.linalg.eigvalsh(gramA).max())
+            _, parts = gather_sum(GA_part)                                    # every rank can read every partial ...
+            g_rows = np.zeros((m_hi - m_lo, K), np.float32)
+            for p in parts:                                                   # ... but sums only ITS rows, rank order
+                g_rows = g_rows + p.numpy()[m_lo:m_hi]
+            rows_new = orc.prox_plus(A[m_lo:m_hi] - step_A * g_rows, step_A)
+            pad = np.zeros((max(b - a for a, b in slices), K), np.float32)     # all-gather of the new rows
+            pad[:m_hi - m_lo] = rows_new
+            recv = [torch.empty_like(torch.from_numpy(pad)) for _ in range(world)]
+            dist.all_gather(recv, torch.from_numpy(pad))
+            A_new = np.concatenate([recv[r].numpy()[:b - a] for r, (a, b) in enumerate(slices)], axis=0)
+            S_new = orc.prox_unity_plus(Sl - step_S * GS, step_S)
+            gramA, _ = gather_sum(rows_new.astype(np.float64).T.dot(rows_new))
+            packed = np.concatenate([S_new.astype(np.float64).dot(S_new.T).ravel(),
+                                     [((S_new - Sl) ** 2).sum(), (S_new ** 2).sum(), (Sl ** 2).sum()]])
+            packed, _ = gather_sum(packed)
+            gramS, nS = packed[:K * K].reshape(K, K), packed[K * K:]
+            A, Sl = A_new, S_new
+        if rank == 0:
+            np.savez(out, A=A, nS=nS)
+        np.save(out + ".S%d.npy" % rank, Sl)
+        np.save(out + ".A%d.npy" % rank, A)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     gramS = allreduce(Sl.astype(np.float64).dot(Sl.T))       # before the first iteration: S S^T of the start point
     for it in range(iters):
         R = A.dot(Sl) - Yl                                   # local stripe of the residual
@@ -71,7 +120,7 @@ def _worker(rank, world, port, out, mode="allreduce"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["allreduce", "gather"])
+@pytest.mark.parametrize("mode", ["allreduce", "gather", "scatter"])
 def test_column_sharded_pgm_matches_unsharded(tmp_path, mode):
     torch = pytest.importorskip("torch")
     import torch.multiprocessing as mp
@@ -79,11 +128,11 @@ def test_column_sharded_pgm_matches_unsharded(tmp_path, mode):
     from oracle import proxmin_oracle as orc
     from proxmin_b200 import workloads
 
-    world, port = 2, 29611 + os.getpid() % 200 + (300 if mode == "gather" else 0)
+    world, port = 2, 29611 + os.getpid() % 200 + {"allreduce": 0, "gather": 300, "scatter": 600}[mode]
     out = str(tmp_path / "res.npz")
     mp.spawn(_worker, args=(world, port, out, mode), nprocs=world, join=True)
     replicas = [np.load(out + ".A%d.npy" % r) for r in range(world)]
-    if mode == "gather":   # rank-ordered sums: bit-identical replicas, the property the peer exchange guarantees
+    if mode in ("gather", "scatter"):   # rank-ordered sums: bit-identical replicas, the property the peer exchange guarantees
         assert all(np.array_equal(replicas[0], a) for a in replicas[1:])
     got = np.load(out)
     S = np.concatenate([np.load(out + ".S%d.npy" % r) for r in range(world)], axis=1)
