@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 return
-            self.stop_flag.wait(0.02)   # (an nvidia-smi query takes 20-40 ms itself: ~20 samples per second)
+            self.stop_flag.wait(0.05)   # (an nvidia-smi query takes 20-40 ms itself: ~10 samples per second)
 
     def summary(self):
         self.stop_flag.set()
