@@ -150,7 +150,7 @@ __global__ void k_peer_sum(pmx_peer_ptrs parts, size_t offset_bytes, size_t n, T
     const unsigned* f = my_flags + set * PMX_MAX_WORLD + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - e) < 0) {
-      if (clock64() - t0 > 6000000000LL) {   // ~3 s of SM clocks: a lost peer must not hang the GPU
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s of SM clocks: a lost peer must not hang the GPU
         if (fault) *fault = 1;
         break;
       }
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) k_small_allreduce(pmx_peer_ptrs arena, si
     const unsigned* f = my_flags + set * PMX_MAX_WORLD + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - e) < 0) {
-      if (clock64() - t0 > 6000000000LL) {   // ~3 s: a lost peer must not hang the GPU
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a lost peer must not hang the GPU
         s_fault = 1;
         break;
       }

@@ -38,7 +38,7 @@ constexpr int TT = 256;
 constexpr int CT_COLS = 32, CT_RPT = 8, CT_LD = 68;   // S tile: 32 columns x 64 rows, stored column-major (ld 68)
 constexpr int RA = PMX_TAIL_RA;                       // rows of A per A block (upper bound; a.ra is the actual count)
 constexpr int NREP = PMX_TAIL_NREP;                   // replicated accumulators of the Gram partials
-constexpr long long SPIN_LIMIT = 6000000000LL;        // ~3 s of SM clocks: a lost peer must not hang the GPU
+constexpr long long SPIN_LIMIT = 20000000000LL;        // ~10 s of SM clocks: a lost peer must not hang the GPU
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
