@@ -527,6 +527,20 @@ def run_admm(args, world, rank, local):
            "d2h_bytes_per_step": int(4 * n / e2e_pass), "passes_executed": e2e_pass,
            "note": "one admm() solve of `steps` iterations on host arrays (LeastSquaresProx / ConstantStep / prox_soft): "
                    "upload of X, b + fused device loop + download of X"}
+    # the same solve through PLAIN Python closures (SURVEY cfg4 / README.md:82-84 spelling): the callback loop, every
+    # library expression one kernel on host arrays that cross PCIe -- reported so that the cost of not using the
+    # recognised helpers (utils.LeastSquaresProx / utils.ConstantStep) is on record
+    closure_rate = None
+    if rank == 0:
+        try:
+            Xc = X0.copy()
+            bc = np.array(b)
+            t0 = time.perf_counter()
+            pmx.admm(Xc, lambda X_, s_: X_ - s_ * (X_ - bc), lambda X_, it=None: 0.5,
+                     prox_g=partial(pmx.prox_soft, thresh=0.5), max_iter=3, e_rel=0)
+            closure_rate = 3.0 / (time.perf_counter() - t0)
+        except Exception as exc:   # diagnostics only
+            closure_rate = "failed: %s" % exc
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -547,6 +561,7 @@ def run_admm(args, world, rank, local):
                                "Python closure for prox_f takes the callback loop (one host round trip per expression)",
                        "l2": "X, Z, U, b = 160 MB > L2 (126 MB); X and U carry an evict_last policy, b and Z evict_first",
                        "passes_executed": n_pass, "restarts": int(restarts.value),
+                       "plain_closure_callback_loop_it_s": closure_rate,
                        "steps": "max_iter = steps; value = executed passes / time (restarts of algorithms.py:503-512 "
                                 "reset the iteration counter)"}}
     emit(args, world, 4, (M, N, K), value, ms / n_pass, launches, clocks, e2e, roof, cpu, extra)
