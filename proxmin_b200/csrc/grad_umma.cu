@@ -66,6 +66,9 @@ namespace {
 #define PMX_WAIT_HINT_NS 0   // suspend-time hint (ns) of the mbarrier waits; 0 = plain try_wait loop.  Round 2: every
                             // hint (100 ns .. 10 ms) costs 6 % -- the wake-up of a suspended warp sits in the tile chain
 #endif
+#ifndef PMX_Y_REFILL_EARLY
+#define PMX_Y_REFILL_EARLY 0   // 1: refill a Y buffer right after the conversion half that consumed it (round-2 experiment)
+#endif
 #ifndef PMX_GS_STACK
 #define PMX_GS_STACK 0
 #endif
@@ -913,6 +916,16 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
           hl[h * 16 + (j >> 1)] = hh;
           hl[h * 16 + 8 + (j >> 1)] = ll;
         }
+#if PMX_Y_REFILL_EARLY
+        // refill the buffer this half just consumed right away (second half of tile t + 1 / first half of tile t + 2)
+        if constexpr (!WGT) {
+          if (h == 0) {
+            if (t + 1 < ntiles) issue_y_half(std::integral_constant<int, YA>{}, nxt, 1, p.Y);
+          } else {
+            if (t + 2 < ntiles) issue_y_half(std::integral_constant<int, YB>{}, nxt2, 0, p.Y);
+          }
+        }
+#endif
         tmem_st16(lane_addr + TM_ACC + slot * 128 + grp * 32 + h * 16, &hl[h * 16]);
       }
       tmem_st_wait();
@@ -957,8 +970,10 @@ k_grad_umma(const __grid_constant__ CUtensorMap tmAhi,
           issue_y_half(IC2{}, nxt, 0, p.W);
         }
       } else {
+#if !PMX_Y_REFILL_EARLY
         if (t + 1 < ntiles) issue_y_half(std::integral_constant<int, YA>{}, nxt, 1, p.Y);
         if (t + 2 < ntiles) issue_y_half(std::integral_constant<int, YB>{}, nxt2, 0, p.Y);
+#endif
       }
       // ---- gradient flushes, one tile behind so that they never wait for the tensor pipe in steady state
       if (t > 0) {
