@@ -412,6 +412,35 @@ def test_matrix_adapter(product):
     assert ident.dot(x) is x and ident.T is ident and ident.spectral_norm == 1
 
 
+def test_tiled_upload_in_column_blocks():
+    """pmx_nmf_set_Y builds the tiled device copy of Y from any column range (the Python front end uploads fp64 /
+    non-contiguous input in column blocks): three ragged ranges must give the same gradients as one upload, for the
+    weight matrix too."""
+    import ctypes as C
+
+    from proxmin_b200 import _ffi, workloads
+    from proxmin_b200 import nmf as pnmf
+
+    Y, A, S = workloads.cfg2(200, 517, 12, seed=4)
+    W = (0.5 + np.random.default_rng(1).random(Y.shape)).astype(np.float32)
+    ref = pnmf.Problem(Y, A, S, W=W)
+    ref.gradient()
+    GA0, GS0 = ref.get(_ffi.GA), ref.get(_ffi.GS)
+    ref.close()
+    prob = pnmf.Problem(np.zeros_like(Y), A, S, W=np.ones_like(W))
+    L = _ffi.lib()
+    for c0, c1 in ((0, 131), (131, 400), (400, 517)):
+        for setter, src in ((L.pmx_nmf_set_Y, Y), (L.pmx_nmf_set_W, W)):
+            part = np.ascontiguousarray(src[:, c0:c1])
+            _ffi.check(setter(prob.handle, part.ctypes.data_as(C.c_void_p), c1 - c0, c0, c1 - c0))
+    prob.gradient()
+    assert np.array_equal(prob.get(_ffi.GA), GA0) and np.array_equal(prob.get(_ffi.GS), GS0)
+    prob.close()
+    Y64 = np.asfortranarray(Y.astype(np.float64))       # fp64, non-contiguous: the column-block path of Problem
+    g64 = pnmf.grad_likelihood(A.astype(np.float64), S.astype(np.float64), Y=Y64, W=W.astype(np.float64))
+    assert g64[0].dtype == np.float64 and np.allclose(g64[0], GA0, rtol=1e-5, atol=1e-4)
+
+
 def test_utils_admm_primitives(product):
     """utils.update_variables / do_the_mm / get_variable_errors / check_constraint_convergence / check_convergence
     (utils.py:295-406) as public functions: one ADMM step with a dense L against the same NumPy expressions."""

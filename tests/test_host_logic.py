@@ -129,3 +129,50 @@ def test_public_names_and_signatures_equal_the_reference():
             elif inspect.isclass(obj) and "__init__" in vars(obj):
                 assert list(inspect.signature(getattr(pmod, n).__init__).parameters)[:len(inspect.signature(obj.__init__).parameters)] \
                     == list(inspect.signature(obj.__init__).parameters), n
+
+
+def test_recognition_of_round2_callables():
+    """operators.describe / algorithms._nmf_grad_target / _linop / _scalar_step on the round-2 additions (host logic
+    only: nothing here touches the device)"""
+    from functools import partial
+
+    from proxmin_b200 import _ffi, algorithms, operators, utils
+
+    assert operators.describe(operators.prox_max_entropy) == [(_ffi.OP_MAXENT, True, 0, 1.0)]
+    assert operators.describe(partial(operators.prox_max_entropy, gamma=2.5, type="absolute")) == \
+        [(_ffi.OP_MAXENT, False, 0, 2.5)]
+    assert operators.describe(partial(operators.prox_max_entropy, gamma=np.ones(3))) is None   # array parameter: host
+    ap = operators.AlternatingProjections([operators.prox_plus, partial(operators.prox_max_entropy, gamma=0.5)])
+    assert [o for (o, _, _, _) in operators.describe(ap)] == [_ffi.OP_MAXENT, _ffi.OP_PLUS]   # reverse list order
+
+    Y = np.ones((4, 6), np.float32)
+    W = np.full((4, 6), 0.5, np.float32)
+    g = partial(pmx.nmf.grad_likelihood, Y=Y)
+    gw = partial(pmx.nmf.grad_likelihood, Y=Y, W=W)
+    assert algorithms._nmf_grad_target(g) is Y
+    assert algorithms._nmf_grad_target(gw) is None                       # the unweighted fused PGM loop must not take it
+    y2, w2 = algorithms._nmf_grad_target(gw, weighted=True)
+    assert y2 is Y and w2 is W
+    assert algorithms._nmf_grad_target(partial(pmx.nmf.grad_likelihood, Y=Y, W=np.ones((3, 3))), weighted=True) == (None, None)
+    assert algorithms._nmf_grad_target(lambda *X: X, weighted=True) == (None, None)
+
+    assert algorithms._linop(None) is None
+    ident = utils.MatrixAdapter(None)
+    assert algorithms._linop(ident) is None and ident.T is ident and ident.spectral_norm == 1
+    x = np.arange(3.0)
+    assert ident.dot(x) is x                                             # NOT a copy (utils.py:70-74)
+    assert algorithms._spec(None) == 1
+    nested = utils.MatrixAdapter(utils.MatrixAdapter(np.eye(2, dtype=np.float32)))   # cascade is unwrapped
+    assert isinstance(nested.L, np.ndarray) and nested.shape == (2, 2) and len(nested) == 2
+
+    assert algorithms._scalar_step(np.float32(0.25)) == 0.25
+    assert algorithms._scalar_step(np.array([0.5])) == 0.5               # BarzilaiBorweinStepper's ndarray of one step
+    with pytest.raises(NotImplementedError):
+        algorithms._scalar_step(np.array([0.5, 0.25]))
+    assert utils.get_step_g(0.5, 4.0, N=2, M=3) == 12.0
+    Z, U = utils.initZU(x, ident)
+    assert Z is not x and np.array_equal(Z, x) and not U.any()
+    with pytest.raises(NameError):
+        operators.prox_components(np.zeros(3), 1.0)
+    with pytest.raises(ValueError):                                      # `if W == 1` on an array (nmf.py:63)
+        pmx.nmf.step_pgm(np.ones((2, 1)), np.ones((1, 2)), W=np.ones((2, 2)))
