@@ -434,7 +434,8 @@ def test_tiled_upload_in_column_blocks():
             part = np.ascontiguousarray(src[:, c0:c1])
             _ffi.check(setter(prob.handle, part.ctypes.data_as(C.c_void_p), c1 - c0, c0, c1 - c0))
     prob.gradient()
-    assert np.array_equal(prob.get(_ffi.GA), GA0) and np.array_equal(prob.get(_ffi.GS), GS0)
+    # (the gradients are accumulated with red.add in an order that varies from launch to launch: last-bit differences)
+    assert np.allclose(prob.get(_ffi.GA), GA0, rtol=2e-6, atol=1e-5) and np.allclose(prob.get(_ffi.GS), GS0, rtol=2e-6, atol=1e-5)
     prob.close()
     Y64 = np.asfortranarray(Y.astype(np.float64))       # fp64, non-contiguous: the column-block path of Problem
     g64 = pnmf.grad_likelihood(A.astype(np.float64), S.astype(np.float64), Y=Y64, W=W.astype(np.float64))
