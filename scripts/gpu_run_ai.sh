@@ -1,0 +1,5 @@
+#!/bin/bash
+# round 2, run AI: full GPU suite on the final tree
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -m gpu -q --timeout 100 -p no:cacheprovider -k "tiled_upload or utils_admm or weighted" > gpurun_out/r2ai_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2ai_pytest.log
+grep -E "passed|failed|FAILED|rc=|^E  " gpurun_out/r2ai_pytest.log | tail -12
