@@ -143,3 +143,99 @@ def test_column_sharded_pgm_matches_unsharded(tmp_path, mode):
     assert np.linalg.norm(got["A"] - A) / np.linalg.norm(A) < 2e-5
     assert np.linalg.norm(S - S0) / np.linalg.norm(S0) < 2e-5
     assert np.allclose(S.sum(axis=0), 1, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# adaprox / AMSGrad column-sharded (BASELINE config 3): the exchange list of nmf_solver.cu's adaprox loop
+# ------------------------------------------------------------------------------------------------------------------
+def _adaprox_worker(rank, world, port, out):
+    """Per iteration the device loop exchanges: sum(G_A partials); the row sums of S (step_adaprox needs the mean over ALL
+    columns, nmf.py:91-93); max(Psi) of the S block (algorithms.py:384, a MAX); per sub-iteration of the S block the two
+    norms of the stopping rule (:389).  The A block is replicated: its moments, Psi and sub-iterations are computed
+    redundantly and must agree bit for bit."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from oracle import proxmin_oracle as orc
+    from proxmin_b200 import workloads
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def gather(x):
+        x = np.ascontiguousarray(x)
+        parts = [torch.empty_like(torch.from_numpy(x)) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(x))
+        return [p.numpy() for p in parts]
+
+    def rank_sum(x):   # k_peer_sum / k_small_allreduce: rank-ordered sum in the working precision
+        acc = np.zeros_like(np.ascontiguousarray(x))
+        for p in gather(x):
+            acc = acc + p
+        return acc
+
+    def rank_max(x):
+        return np.max(np.stack(gather(np.atleast_1d(x))), axis=0)[0]
+
+    M, N, K = 64, 300, 5
+    Y, A, S = workloads.cfg2(M, N, K, seed=13)
+    lo, hi = workloads.shard_columns(N, world, rank, align=128)
+    Yl, Sl, A = Y[:, lo:hi].copy(), S[:, lo:hi].copy(), A.copy()
+    iters, b2, eps, p, e_rel = 12, 0.999, 1e-8, 0.25, 1e-3
+    b1 = np.array((0.9,) * iters)
+    MA, VA = np.zeros_like(A), np.zeros_like(A)
+    MS, VS = np.zeros_like(Sl), np.zeros_like(Sl)
+    sub = [0, 0]
+    for it in range(iters):
+        R = A.dot(Sl) - Yl
+        GA = rank_sum(R.dot(Sl.T))                                        # exchange 1: G_A partials
+        GS = A.T.dot(R)
+        alphaA = np.mean(A, axis=0) / 10                                   # nmf.py:91-93
+        rows = rank_sum(Sl.astype(np.float64).sum(axis=1))                 # exchange 2: row sums of S over all columns
+        alphaS = (rows / N).astype(np.float32)[:, None] / 10
+        for j, (X, G, Mj, Vj, al) in enumerate(((A, GA, MA, VA, alphaA), (Sl, GS, MS, VS, alphaS))):
+            Phi, Psi = orc._phi_psi("amsgrad", it, G, Mj, Vj, None, b1, b2, eps, p)
+            X[:] -= al * Phi / Psi
+            z = X.copy()
+            psimax = np.max(Psi) if j == 0 else rank_max(np.max(Psi))      # exchange 3: max Psi of the sharded block
+            gamma = al / psimax
+            for tau in range(1, 1001):
+                z_new = orc.prox_plus(z - gamma / al * Psi * (z - X), gamma)
+                nd, nz = orc.l2sq(z_new - z), orc.l2sq(z)
+                if j == 1:                                                 # exchange 4: the sub-iteration norms
+                    nd, nz = rank_sum(np.array([nd, nz], dtype=np.float64))
+                z = z_new
+                if np.float32(nd) <= np.float32(e_rel ** 2) * np.float32(nz):
+                    break
+            sub[j] += tau
+            X[:] = z
+    np.save(out + ".S%d.npy" % rank, Sl)
+    np.save(out + ".A%d.npy" % rank, A)
+    np.save(out + ".sub%d.npy" % rank, np.array(sub))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_sharded_adaprox_matches_unsharded(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+
+    from oracle import proxmin_oracle as orc
+    from proxmin_b200 import workloads
+
+    world, port = 2, 30311 + os.getpid() % 200
+    out = str(tmp_path / "ada")
+    mp.spawn(_adaprox_worker, args=(world, port, out), nprocs=world, join=True)
+    replicas = [np.load(out + ".A%d.npy" % r) for r in range(world)]
+    assert all(np.array_equal(replicas[0], a) for a in replicas[1:])       # rank-ordered sums: bit-identical replicas
+    subs = [np.load(out + ".sub%d.npy" % r) for r in range(world)]
+    assert all(np.array_equal(subs[0], s_) for s_ in subs[1:])             # same stopping decisions on every rank
+    S = np.concatenate([np.load(out + ".S%d.npy" % r) for r in range(world)], axis=1)
+    M, N, K = 64, 300, 5
+    Y, A, S0 = workloads.cfg2(M, N, K, seed=13)
+    res = orc.nmf(Y, A, S0, algorithm="adaprox", scheme="amsgrad", max_iter=12, check_convergence=False)
+    assert list(res[5]) == list(subs[0])                                   # sub-iteration counts of the unsharded run
+    assert np.linalg.norm(replicas[0] - A) / np.linalg.norm(A) < 2e-5
+    assert np.linalg.norm(S - S0) / np.linalg.norm(S0) < 2e-5
