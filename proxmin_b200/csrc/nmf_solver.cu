@@ -262,6 +262,7 @@ int nmf_global_cols(pmx_nmf* h) {
 extern "C" {
 
 static int tail_publish_G(pmx_nmf* h);
+static int tail_detach(pmx_nmf* h);
 
 int pmx_nmf_create(pmx_ctx* ctx, int M, int N_local, int K, pmx_nmf** out) {
   PMX_REQUIRE(ctx && out, "NULL argument");
@@ -397,6 +398,7 @@ int pmx_nmf_set_W(pmx_nmf* h, const float* host_W, size_t ld, int col0, int ncol
 
 int pmx_nmf_gradient(pmx_nmf* h, double* loss_host_or_null) {
   PMX_REQUIRE(h != nullptr, "NULL argument");
+  PMX_CHECK(tail_detach(h));
   h->tail_G_pending = false;
   double* dl = loss_host_or_null ? &h->ctl->norms[6] : nullptr;
   PMX_CHECK(nmf_gradient(h, h->A, h->S, h->GA, h->GS, dl, 0, nullptr));
@@ -459,8 +461,21 @@ int pmx_nmf_device_ptr(pmx_nmf* h, int which, float** dev_ptr) {
   return which_ptr(h, which, dev_ptr, &n);
 }
 
+// A sharded fused-tail solve leaves the plan's A operands pointing into the peer arena (every rank's tail pushes its
+// rows there).  Anything that evaluates the gradient kernel outside that loop must not depend on the arena -- another
+// solve may re-lay it out: back to the plan's own buffers, operands re-split from h->A on the next launch.
+static int tail_detach(pmx_nmf* h) {
+  if (h->tail_mode && h->ctx->world > 1 && h->plan) {
+    PMX_CHECK(umma_plan_use_A(h->plan, nullptr, nullptr));
+    h->split_valid = false;
+    h->tail_ready = false;
+  }
+  return PMX_OK;
+}
+
 int pmx_nmf_loss(pmx_nmf* h, double* loss_host) {
   PMX_REQUIRE(h && loss_host, "NULL argument");
+  PMX_CHECK(tail_detach(h));
   // the loss is a by-product of the residual pass: the tcgen05 kernel runs it alone (no gradient GEMMs, no flush,
   // no scratch); the SIMT kernel (tiny problems) still produces both gradients into scratch buffers
   int st;
